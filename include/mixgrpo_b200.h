@@ -1,0 +1,184 @@
+/*
+ * mixgrpo_b200 — C ABI of the B200-native MixGRPO rollout / policy-update hot path.
+ *
+ * The reference (zqqqqz2000/MixGRPO) has no FFI: its boundary for this path is a set of Python
+ * functions operating on torch tensors (fastvideo/utils/sampling_utils.py, "SU") and inline
+ * arithmetic in fastvideo/train_grpo_flux.py ("TR").  This header is the plain-C boundary a
+ * binding (ctypes / cffi / pybind / TORCH_LIBRARY shim) attaches to; every entry point names
+ * the reference code it replaces.  No torch types appear here: device pointers, sizes, a
+ * coefficient block and a cudaStream_t (as void*) only.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are (B, n) row-major: B samples of n = S*64 packed-latent scalars; a "batch
+ *     stride" (in elements) lets a view such as all_latents[:, i] (SU:153) be read/written in
+ *     place; pass n for a contiguous tensor;
+ *   - every function returns 0 on success, a cudaError_t (>0) when the launch failed, or a
+ *     negative MIXGRPO_E* code for argument errors.  Nothing throws, nothing synchronises;
+ *   - kernels are launched on `stream`; all are CUDA-graph capturable;
+ *   - there is NO CPU fallback: without a CUDA device the calls fail.
+ */
+#ifndef MIXGRPO_B200_H
+#define MIXGRPO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIXGRPO_ABI_VERSION 1
+
+/* element type of model_output / noise / grad_model_output */
+enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
+
+/* where x_next comes from */
+enum {
+  MIXGRPO_SRC_NOISE = 0,        /* rollout, SDE:  x_next = mean + scale*noise   (SU:188-195, SU:238, SU:434) */
+  MIXGRPO_SRC_GIVEN = 1,        /* policy update: x_next supplied (prev_sample=, TR:149-157)               */
+  MIXGRPO_SRC_DETERMINISTIC = 2 /* rollout, ODE:  Euler / DPM closed form       (SU:198-199, SU:240, SU:436) */
+};
+
+/* flags */
+#define MIXGRPO_FLAG_ROUND_LIKE_TORCH 1u /* reproduce torch's bf16 type-promotion roundings */
+
+/* error codes */
+#define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
+#define MIXGRPO_EALIGN   (-2)  /* reserved */
+#define MIXGRPO_ENOSPACE (-3)  /* workspace too small */
+
+/* Per-step scalar block.  All values are fp32 numbers computed on the HOST with the reference's
+ * operator order (mixgrpo_b200/coefs.py); where torch would cast a 0-dim scalar to bf16 before a
+ * multiply, the host stores the already-rounded value.  Layout per family:
+ *
+ *  common (all families)
+ *    two_var   2*scale^2            divisor of the squared residual          (SU:202, SU:245, SU:377)
+ *    log_scale log(scale)           0 for the dance family (SU:247 quirk)
+ *    log_norm  log(sqrt(2*pi))      0 for the dance family
+ *
+ *  flow  (flow_grpo_step, SU:157-210)         c[0..5]
+ *    0 sigma   (x0 = x - sigma*v)               1 c_x  = 1 + std^2/(2 sigma)*dt
+ *    2 c_v   = 1 + std^2 (1-sigma)/(2 sigma)    3 dt   (factor of the mean's v term)
+ *    4 scale = std*sqrt(-dt) (noise factor)     5 dt   (Euler ODE factor, SU:199)
+ *
+ *  dance (dance_grpo_step, SU:212-253)        c[0..6]
+ *    0 sigma (x0)   1 dsigma (mean = x + dsigma*v)   2 1-sigma   3 sigma^2
+ *    4 -0.5*eta^2   5 dsigma (drift factor, fp32)    6 std = eta*sqrt(-dsigma)
+ *
+ *  dpm   (dpm_step and its order-1/2/3 updates, SU:273-639)   c[0..13]
+ *    0 sigma_s (x0 = x - sigma_s*v, SU:394)
+ *    1 1/r0     2 1/r1     3 r0/(r0+r1)    4 1/(r0+r1)          (finite differences, SU:490, SU:608-610)
+ *    5..8   mean   = c5*x + c6*D0 + c7*D1 + c8*D2                (signs folded into the coefficients)
+ *    9..12  x_ode  = c9*x + c10*D0 + c11*D1 + c12*D2
+ *    13 scale = sigma_t*sqrt(1-exp(-2h))  (noise factor)
+ */
+typedef struct mixgrpo_step_coefs {
+  float two_var;
+  float log_scale;
+  float log_norm;
+  float c[16];
+} mixgrpo_step_coefs;
+
+/* Bytes of zero-initialised device workspace the step kernels need for (B, n).  The block holds the
+ * per-sample arrival counters and the per-CTA partial sums of the deterministic log-prob reduction;
+ * kernels leave the counters zeroed again, so one allocation can be reused by successive launches
+ * on the same stream. */
+int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
+
+/* ABI / build introspection. */
+int mixgrpo_abi_version(void);
+const char* mixgrpo_build_info(void);          /* e.g. "sm_100a nvcc 12.9 ..." (static string) */
+int mixgrpo_set_tuning(int key, int value);    /* bench-only knobs; returns previous value or <0 */
+const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGetErrorString for >0) */
+
+/* ---- fused sampler step + Gaussian transition log-prob ---------------------------------------
+ * One pass over the latents: reads v (and noise or the stored x_next), writes x_next / x0
+ * (/ mean) and the per-sample log-prob.  Output pointers may be NULL to skip that stream.
+ *
+ * mixgrpo_flow_step   replaces flow_grpo_step            SU:157-210 (rollout SU:85-93; train TR:149-157)
+ * mixgrpo_dance_step  replaces dance_grpo_step           SU:212-253 (rollout SU:95-98; train TR:159-168)
+ * mixgrpo_dpm_step    replaces dpm_step + convert_model_output + order-1/2/3 updates
+ *                              SU:273-639 (rollout SU:101-111, SU:135-144; train TR:170-180)
+ *
+ *   v, v_dtype      model_output (B,n), contiguous, MIXGRPO_F32 | MIXGRPO_BF16
+ *   x, x_bs         latents fp32 (B,n) with batch stride x_bs
+ *   noise           src==NOISE: (B,n) contiguous; dtype v_dtype for flow, fp32 for dance/dpm
+ *   x_next_in,in_bs src==GIVEN: stored next latents fp32
+ *   m1, m2          dpm order>=2 / ==3: previous x0 predictions fp32 (B,n) contiguous (DPMState, SU:255-271)
+ *   x_next_out,out_bs   fp32 (B,n) or NULL      x0_out  fp32 (B,n) contiguous or NULL
+ *   mean_out        fp32 (B,n) contiguous or NULL (the 5-tuple's prev_sample_mean, SU:210)
+ *   logp_out        fp32 [B] or NULL
+ *   workspace       >= mixgrpo_step_workspace_bytes(B,n), zeroed once at allocation
+ */
+int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
+                      const void* noise, const float* x_next_in, int64_t in_bs,
+                      float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
+                      float* logp_out, void* workspace, int64_t workspace_bytes,
+                      int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                      int src, unsigned flags, void* stream);
+
+int mixgrpo_dance_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
+                       const float* noise, const float* x_next_in, int64_t in_bs,
+                       float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
+                       float* logp_out, void* workspace, int64_t workspace_bytes,
+                       int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                       int src, int sde_solver, unsigned flags, void* stream);
+
+int mixgrpo_dpm_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
+                     const float* noise, const float* m1, const float* m2, int order,
+                     float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
+                     float* logp_out, void* workspace, int64_t workspace_bytes,
+                     int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                     int src, unsigned flags, void* stream);
+
+/* ---- backward of the transition log-prob w.r.t. model_output ----------------------------------
+ * Replaces autograd through SU:175-208 / SU:224-250 when TR:585 calls loss.backward():
+ *   grad_v = dL/dlogp[b] * (x_next - mean)/scale^2 * dmean/dv / n      (closed form)
+ * mean is recomputed from (v, x) in the same pass; grad_logp is a DEVICE vector [B], so no host
+ * sync sits between the loss kernel and this one.  grad_v has dtype v_dtype.
+ * family: 0 flow, 1 dance (sde_solver=True, the only trained variant TR:159-168). */
+int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                        const float* x_next, int64_t in_bs, const float* grad_logp,
+                        void* grad_v, int64_t B, int64_t n,
+                        const mixgrpo_step_coefs* coefs_host, unsigned flags, void* stream);
+
+/* ---- reward -> group-relative advantage -------------------------------------------------------
+ * Replaces TR:439-501.  rewards is [n_models, local_B] fp32 (one all-gathered or rank-local
+ * matrix), groups are consecutive runs of num_generations samples (TR:444-450).
+ *   A[b] = sum_m w[m] * (r[m,b] - mean_g) / (std_g + 1e-8),  std Bessel-corrected (TR:459-461)
+ * trim_size > 0: mean/std over the group's rewards with the trim_size smallest removed (TR:451-457).
+ * use_group == 0: single-model global normalisation with statistics of `stat_rewards`
+ * [n_stat] (the all-gathered vector, TR:498).  weights may be NULL only when n_models == 1
+ * (reward_aggr, TR:470-491: the advantage is stored unweighted). */
+int mixgrpo_group_advantages(const float* rewards, const float* weights, int n_models,
+                             int64_t local_B, int num_generations, int trim_size,
+                             int use_group, const float* stat_rewards, int64_t n_stat,
+                             float* advantages, void* stream);
+
+/* ---- clipped-ratio GRPO loss, forward + closed-form backward ---------------------------------
+ * Replaces TR:560-583 and the scalar part of TR:585.  All vectors are [B] fp32 on the device.
+ *   stats_out[0..3] = loss, policy_loss, kl_loss, clip_frac          (TR:575-583)
+ *   grad_new_logp[b] = dloss/dnew_logp[b]  (may be NULL)
+ * denom = gradient_accumulation_steps * len(train_timesteps) (TR:576).  The four scalars are the
+ * python floats of the reference call site (doubles); they are narrowed to fp32 exactly where torch
+ * narrows them (clamp bounds 1-clip / 1+clip are formed in double first, TR:571-572).
+ * stats_accum (nullable, [4]) += stats_out: device-side running sums replacing the four
+ * all_reduce+.item() pairs per (sample, step) at TR:586-600. */
+int mixgrpo_grpo_loss(const float* new_logp, const float* old_logp, const float* advantages,
+                      int64_t B, double clip_range, double adv_clip_max, double kl_coeff, double denom,
+                      float* stats_out, float* grad_new_logp, float* stats_accum, void* stream);
+
+/* ---- layout helpers either side of the path ----------------------------------------------------
+ * mixgrpo_pack_latents    (B,C,H,W) -> (B,(H/2)(W/2),4C)     TR:94-99   (src dtype bf16|f32 -> same)
+ * mixgrpo_unpack_latents  inverse, fused with the VAE de-normalisation  x/divisor + shift
+ *                         (TR:102-115 then TR:287 `latents / 0.3611 + 0.1159`; pass divisor=1, shift=0
+ *                         for the plain permute).  H, W are the UNPACKED latent height/width. */
+int mixgrpo_pack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W,
+                         void* stream);
+int mixgrpo_unpack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W,
+                           float divisor, float shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXGRPO_B200_H */

@@ -1,0 +1,78 @@
+"""ctypes binding of ``include/mixgrpo_b200.h`` — the only way Python reaches the CUDA kernels.
+
+There is NO fallback: if the shared library is missing and cannot be built, or a call returns a
+non-zero code, a ``RuntimeError`` is raised.  Nothing in here imports ``oracle``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from . import _build
+
+F32, BF16 = 0, 1
+SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC = 0, 1, 2
+FLAG_ROUND_LIKE_TORCH = 1
+ABI_VERSION = 1
+
+
+class StepCoefs(C.Structure):
+    """mirror of ``mixgrpo_step_coefs`` (include/mixgrpo_b200.h)."""
+    _fields_ = [("two_var", C.c_float), ("log_scale", C.c_float), ("log_norm", C.c_float), ("c", C.c_float * 16)]
+
+
+_P, _I64, _I, _U, _F, _D = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float, C.c_double
+_CP = C.POINTER(StepCoefs)
+
+# name -> (restype, argtypes); every symbol include/mixgrpo_b200.h declares
+SIGNATURES = {
+    "mixgrpo_step_workspace_bytes": (_I64, [_I64, _I64]),
+    "mixgrpo_abi_version": (_I, []),
+    "mixgrpo_build_info": (C.c_char_p, []),
+    "mixgrpo_set_tuning": (_I, [_I, _I]),
+    "mixgrpo_error_string": (C.c_char_p, [_I]),
+    "mixgrpo_flow_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P]),
+    "mixgrpo_dance_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _I, _U, _P]),
+    "mixgrpo_dpm_step": (_I, [_P, _I, _P, _I64, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P]),
+    "mixgrpo_logprob_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _CP, _U, _P]),
+    "mixgrpo_group_advantages": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P, _I64, _P, _P]),
+    "mixgrpo_grpo_loss": (_I, [_P, _P, _P, _I64, _D, _D, _D, _D, _P, _P, _P, _P]),
+    "mixgrpo_pack_latents": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P]),
+    "mixgrpo_unpack_latents": (_I, [_P, _P, _I, _I64, _I, _I, _I, _F, _F, _P]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return str(_build.LIB)
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the in-tree .so is missing or stale and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _build.LIB.exists() or (not _build.is_fresh() and os.environ.get("MIXGRPO_NO_REBUILD") != "1"):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not _build.LIB.exists():
+                raise RuntimeError(
+                    f"mixgrpo_b200: CUDA library {_build.LIB} is missing and could not be built ({e}). "
+                    "There is no CPU fallback; run `python -c 'import __graft_entry__ as g; g.build()'`.") from e
+    h = C.CDLL(str(_build.LIB))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)          # AttributeError here = the .so does not export the header's symbol
+        fn.restype, fn.argtypes = res, args
+    if h.mixgrpo_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"mixgrpo_b200: ABI mismatch (lib {h.mixgrpo_abi_version()} != binding {ABI_VERSION})")
+    _lib = h
+    return h
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().mixgrpo_error_string(rc).decode()
+        raise RuntimeError(f"mixgrpo_b200: {what} failed with code {rc}: {msg}")

@@ -1,0 +1,128 @@
+// Backward of the transition log-prob w.r.t. model_output (policy update, TR:585 loss.backward()
+// flowing through SU:175-208 / SU:224-250).  One streaming pass: read v, x, x_next (10 B/elem with
+// bf16 v), recompute the mean exactly as the forward did, write grad_v (2 B/elem).
+//
+// Autograd chain being reproduced (g = dL/dlogp[b], n = elements per sample, d = x_next - mean):
+//   mean(dim)        -> g/n
+//   (.)/(2 s^2)      -> (g/n)/(2 s^2)
+//   -(d^2)           -> that * (2 d)          and d = x_next.detach() - mean gives +1 overall
+//   flow : mean = x*c_x + (v*c_v)*dt          -> grad_v = ((gm)*dt)*c_v        (bf16 at every step
+//   dance: mean = x + ds*v + drift(x0(v))*ds  -> two bf16 contributions summed  when v is bf16)
+#include "common.cuh"
+
+namespace mg {
+
+struct BwdParams {
+  const void* v;
+  const float* x;
+  const float* x_next;
+  const float* grad_logp;
+  void* grad_v;
+  long long n, x_bs, in_bs;
+  mixgrpo_step_coefs k;
+};
+
+template <int FAM, class VT, bool RND, int VEC>
+__global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_constant__ BwdParams p) {
+  const int b = blockIdx.y;
+  const long long idx = ((long long)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (idx >= p.n) return;
+  const float* c = p.k.c;
+  float v[VEC], x[VEC], xn[VEC], t[VEC], mu[VEC], x0[VEC], g[VEC];
+  ld_stream(reinterpret_cast<const VT*>(p.v) + (long long)b * p.n + idx, v);
+  ld_stream(p.x + (long long)b * p.x_bs + idx, x);
+  ld_stream(p.x_next + (long long)b * p.in_bs + idx, xn);
+  // (g/n)/(2 s^2): per-sample scalar, same two divisions autograd performs
+  const float gs = __fdiv_rn(__fdiv_rn(__ldg(p.grad_logp + b), (float)p.n), p.k.two_var);
+
+  if constexpr (FAM == 0) {   // flow, SU:186
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(v[i], c[2]);
+    round_like_torch<RND>(t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(t[i], c[3]);
+    round_like_torch<RND>(t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      mu[i] = __fadd_rn(__fmul_rn(x[i], c[1]), t[i]);
+      g[i] = __fmul_rn(gs, __fmul_rn(2.f, __fsub_rn(xn[i], mu[i])));
+    }
+    round_like_torch<RND>(g);                      // grad of the bf16 term
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = __fmul_rn(g[i], c[3]);
+    round_like_torch<RND>(g);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = __fmul_rn(g[i], c[2]);
+  } else {                    // dance with sde_solver=True, SU:224-234
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(c[0], v[i]);
+    round_like_torch<RND>(t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) x0[i] = __fsub_rn(x[i], t[i]);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(c[1], v[i]);
+    round_like_torch<RND>(t);
+    float g1[VEC], g2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float m = __fadd_rn(x[i], t[i]);
+      float s = __fdiv_rn(-__fsub_rn(x[i], __fmul_rn(x0[i], c[2])), c[3]);
+      m = __fadd_rn(m, __fmul_rn(__fmul_rn(s, c[4]), c[5]));
+      const float gm = __fmul_rn(gs, __fmul_rn(2.f, __fsub_rn(xn[i], m)));
+      g1[i] = gm;                                                     // via mean = x + ds*v
+      // via drift: gm*ds -> *k -> /sigma^2 -> (two negations cancel) -> *(1-sigma) -> x0 = x - sigma*v
+      g2[i] = -__fmul_rn(__fdiv_rn(__fmul_rn(__fmul_rn(gm, c[5]), c[4]), c[3]), c[2]);
+    }
+    round_like_torch<RND>(g1);
+    round_like_torch<RND>(g2);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { g1[i] = __fmul_rn(g1[i], c[1]); g2[i] = __fmul_rn(g2[i], c[0]); }
+    round_like_torch<RND>(g1);
+    round_like_torch<RND>(g2);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = __fadd_rn(g1[i], g2[i]);
+  }
+  st_stream(reinterpret_cast<VT*>(p.grad_v) + (long long)b * p.n + idx, g);   // bf16 store rounds (RNE)
+}
+
+template <int FAM, class VT, bool RND>
+static int launch_bwd(const BwdParams& p, int64_t B, bool vec, cudaStream_t st) {
+  if (vec) {
+    dim3 grid((unsigned)((p.n + (long long)kThreads * kVec - 1) / ((long long)kThreads * kVec)), (unsigned)B);
+    logprob_bwd_kernel<FAM, VT, RND, kVec><<<grid, kThreads, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)((p.n + kThreads - 1) / kThreads), (unsigned)B);
+    logprob_bwd_kernel<FAM, VT, RND, 1><<<grid, kThreads, 0, st>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+template <int FAM>
+static int bwd_family(const BwdParams& p, int v_dtype, int64_t B, bool vec, bool rnd, cudaStream_t st) {
+  if (v_dtype == MIXGRPO_F32) return launch_bwd<FAM, float, false>(p, B, vec, st);
+  if (rnd) return launch_bwd<FAM, __nv_bfloat16, true>(p, B, vec, st);
+  return launch_bwd<FAM, __nv_bfloat16, false>(p, B, vec, st);
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                                   const float* x_next, int64_t in_bs, const float* grad_logp, void* grad_v,
+                                   int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, unsigned flags,
+                                   void* stream) {
+  if (!v || !x || !x_next || !grad_logp || !grad_v || !coefs_host || B <= 0 || B > 65535 || n <= 0) return MIXGRPO_EINVAL;
+  if (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) return MIXGRPO_EINVAL;
+  if (family != 0 && family != 1) return MIXGRPO_EINVAL;
+  BwdParams p;
+  p.v = v; p.x = x; p.x_next = x_next; p.grad_logp = grad_logp; p.grad_v = grad_v;
+  p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.k = *coefs_host;
+  auto al = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
+  const size_t va = v_dtype == MIXGRPO_BF16 ? 16 : 32;
+  const bool vec = (n % kVec == 0) && (x_bs % kVec == 0) && (in_bs % kVec == 0) && al(v, va) && al(grad_v, va) &&
+                   al(x, 32) && al(x_next, 32);
+  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return family == 0 ? bwd_family<0>(p, v_dtype, B, vec, rnd, st) : bwd_family<1>(p, v_dtype, B, vec, rnd, st);
+}

@@ -1,0 +1,114 @@
+// Shared device helpers for the mixgrpo_b200 streaming kernels (sm_100a only).
+//
+// The hot path is HBM-bound elementwise + reduction work (≈1 flop/byte), so everything here is
+// about moving bytes: 256-bit LDG/STG (sm_100 adds .v8.f32 / LDG.E.256) so that one thread owns 8
+// consecutive latent scalars in every stream — 32 B of fp32, 16 B of bf16 — and every warp-level
+// request covers whole 128-B lines with all sectors used; streaming (no-L1-allocate) hints; a
+// deterministic warp-shuffle → shared → last-CTA reduction for the per-sample log-prob.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mixgrpo_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "mixgrpo_b200 kernels target sm_100a (B200) only"
+#endif
+
+namespace mg {
+
+constexpr int kThreads = 256;   // threads per CTA for the streaming kernels
+constexpr int kVec = 8;         // latent scalars owned by one thread per tile
+constexpr int kMaxPartials = 4096;
+
+// ---------------------------------------------------------------- 256/128-bit streaming access
+__device__ __forceinline__ void ld_stream(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_stream(const float* p, float (&r)[1]) { r[0] = __ldg(p); }
+
+// 8 bf16 (16 B) -> 8 floats.  Widening is exact: bf16 is the top half of an fp32.
+__device__ __forceinline__ void ld_stream(const __nv_bfloat16* p, float (&r)[8]) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+               : "l"(p));
+  r[0] = __uint_as_float(a << 16); r[1] = __uint_as_float(a & 0xffff0000u);
+  r[2] = __uint_as_float(b << 16); r[3] = __uint_as_float(b & 0xffff0000u);
+  r[4] = __uint_as_float(c << 16); r[5] = __uint_as_float(c & 0xffff0000u);
+  r[6] = __uint_as_float(d << 16); r[7] = __uint_as_float(d & 0xffff0000u);
+}
+__device__ __forceinline__ void ld_stream(const __nv_bfloat16* p, float (&r)[1]) {
+  r[0] = __bfloat162float(*p);
+}
+
+__device__ __forceinline__ void st_stream(float* p, const float (&r)[8]) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(float* p, const float (&r)[1]) { *p = r[0]; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);   // .x = lo (low half-word), .y = hi
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, const float (&r)[8]) {
+  uint32_t a = pack_bf16x2(r[0], r[1]), b = pack_bf16x2(r[2], r[3]);
+  uint32_t c = pack_bf16x2(r[4], r[5]), d = pack_bf16x2(r[6], r[7]);
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, const float (&r)[1]) {
+  *p = __float2bfloat16_rn(r[0]);
+}
+
+// ---------------------------------------------------------------- torch-promotion rounding
+// R<RND>(x): when torch's type promotion would have produced a bf16 intermediate, round x to bf16
+// (RNE, like c10::BFloat16) and widen back.  Pairs share one F2FP.BF16.F32.PACK_AB.
+template <bool RND, int N>
+__device__ __forceinline__ void round_like_torch(float (&r)[N]) {
+  if constexpr (RND) {
+    if constexpr (N % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < N; k += 2) {
+        uint32_t u = pack_bf16x2(r[k], r[k + 1]);
+        r[k] = __uint_as_float(u << 16);
+        r[k + 1] = __uint_as_float(u & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) r[k] = __bfloat162float(__float2bfloat16_rn(r[k]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- deterministic reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA, result valid in every thread of warp 0 (fixed tree => bitwise reproducible).
+__device__ __forceinline__ float block_sum(float v, float* s_warp /* [kThreads/32] */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (warp == 0) {
+    t = lane < (kThreads / 32) ? s_warp[lane] : 0.f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// workspace layout: [B uint32 counters, padded to 256 B][B * nblk float partials]
+__host__ __device__ inline int64_t ws_counter_bytes(int64_t B) { return ((B * 4 + 255) / 256) * 256; }
+
+}  // namespace mg

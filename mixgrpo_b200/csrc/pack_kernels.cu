@@ -1,0 +1,86 @@
+// Layout helpers either side of the sampler path: FLUX 2x2 patchify of VAE latents
+//   pack   (B,C,H,W) -> (B,(H/2)(W/2),4C)   TR:94-99
+//   unpack inverse, optionally fused with the VAE de-normalisation x/0.3611 + 0.1159   TR:102-115, TR:287
+// TR = /root/reference/fastvideo/train_grpo_flux.py.  Pure permutes (HBM-bound, 2x element size per
+// element); one thread moves one 2-element row fragment so both sides see >= 8-byte accesses for fp32.
+#include "common.cuh"
+
+namespace mg {
+
+// packed index: [b][hp][wp][c][dh][dw]   <->   unpacked: [b][c][2hp+dh][2wp+dw]
+template <class T, bool PACK, bool AFFINE>
+__global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ src, T* __restrict__ dst, long long total_pairs,
+                                                  int C, int H, int W, float divisor, float shift) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // one (dw=0,1) pair
+  if (i >= total_pairs) return;
+  const int Wp = W / 2, Hp = H / 2;
+  // enumerate in PACKED order so the packed side is fully coalesced
+  long long r = i;
+  const int dh = (int)(r % 2); r /= 2;
+  const int c = (int)(r % C); r /= C;
+  const int wp = (int)(r % Wp); r /= Wp;
+  const int hp = (int)(r % Hp); r /= Hp;
+  const long long b = r;
+  const long long packed = i * 2;
+  const long long unpacked = ((b * C + c) * H + (2 * hp + dh)) * (long long)W + 2 * wp;
+  if constexpr (PACK) {
+    dst[packed] = src[unpacked];
+    dst[packed + 1] = src[unpacked + 1];
+  } else {
+    float a0 = (float)src[packed], a1 = (float)src[packed + 1];
+    if constexpr (AFFINE) {
+      a0 = __fadd_rn(__fdiv_rn(a0, divisor), shift);
+      a1 = __fadd_rn(__fdiv_rn(a1, divisor), shift);
+    }
+    dst[unpacked] = (T)a0;
+    dst[unpacked + 1] = (T)a1;
+  }
+}
+
+template <bool PACK>
+static int launch_pack(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W, float divisor, float shift,
+                       cudaStream_t st) {
+  if (!src || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H % 2) || (W % 2)) return MIXGRPO_EINVAL;
+  const long long pairs = (long long)B * C * H * W / 2;
+  const unsigned grid = (unsigned)((pairs + 255) / 256);
+  const bool affine = !PACK && !(divisor == 1.f && shift == 0.f);
+  if (dtype == MIXGRPO_F32) {
+    if (affine) pack_kernel<float, PACK, true><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
+    else pack_kernel<float, PACK, false><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
+  } else if (dtype == MIXGRPO_BF16) {
+    if (affine) pack_kernel<__nv_bfloat16, PACK, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
+    else pack_kernel<__nv_bfloat16, PACK, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
+  } else {
+    return MIXGRPO_EINVAL;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace mg
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_pack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W, void* stream) {
+  return mg::launch_pack<true>(src, dst, dtype, B, C, H, W, 1.f, 0.f, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_unpack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W, float divisor,
+                                      float shift, void* stream) {
+  return mg::launch_pack<false>(src, dst, dtype, B, C, H, W, divisor, shift, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_abi_version(void) { return MIXGRPO_ABI_VERSION; }
+
+#define MG_STR2(x) #x
+#define MG_STR(x) MG_STR2(x)
+extern "C" __attribute__((visibility("default"))) const char* mixgrpo_build_info(void) {
+  return "mixgrpo_b200 abi " MG_STR(MIXGRPO_ABI_VERSION) " sm_100a nvcc " MG_STR(__CUDACC_VER_MAJOR__) "." MG_STR(__CUDACC_VER_MINOR__) " built " __DATE__;
+}
+
+extern "C" __attribute__((visibility("default"))) const char* mixgrpo_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case MIXGRPO_EINVAL: return "mixgrpo: invalid argument";
+    case MIXGRPO_EALIGN: return "mixgrpo: misaligned pointer";
+    case MIXGRPO_ENOSPACE: return "mixgrpo: workspace too small";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "mixgrpo: unknown error";
+  }
+}

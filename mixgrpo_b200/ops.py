@@ -1,0 +1,282 @@
+"""Tensor-level wrappers over the C ABI (``include/mixgrpo_b200.h``): argument validation, output
+allocation through torch's caching allocator, workspace management, stream plumbing.
+
+Everything here launches hand-written sm_100a kernels from ``csrc/``.  CPU tensors are rejected — there
+is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import BF16, F32, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, StepCoefs
+
+FLOW, DANCE, DPM = 0, 1, 2
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+#: number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RuntimeError(f"mixgrpo_b200: `{name}` must be a CUDA tensor — this package has no CPU fallback "
+                           f"(got {getattr(t, 'device', type(t))})")
+
+
+def _dtype_code(t: torch.Tensor, name: str) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"mixgrpo_b200: `{name}` must be float32 or bfloat16, got {t.dtype}")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _rows(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Return (tensor, batch stride in elements) for a (B, ...) tensor whose per-sample block is
+    contiguous; anything else is made contiguous (one copy)."""
+    if t.dim() < 1:
+        raise ValueError(f"mixgrpo_b200: `{name}` needs a batch dimension")
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.shape[0] == 1:
+        return (t if t[0].is_contiguous() else t.contiguous()), t[0].numel()
+    if t[0].is_contiguous():
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.stride(0)
+
+
+def _workspace(device: torch.device, B: int, n: int) -> torch.Tensor:
+    need = _cabi.lib().mixgrpo_step_workspace_bytes(B, n)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)   # counters must start at zero
+        _workspaces[key] = ws
+    return ws
+
+
+def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, *, src: int,
+               noise: Optional[torch.Tensor] = None, x_next: Optional[torch.Tensor] = None,
+               m1: Optional[torch.Tensor] = None, m2: Optional[torch.Tensor] = None, order: int = 1,
+               sde_solver: bool = True, out_x_next: Optional[torch.Tensor] = None, want_x0: bool = True,
+               want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
+               out_logp: Optional[torch.Tensor] = None):
+    """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
+    requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in."""
+    global launch_count
+    lib = _cabi.lib()
+    _require_cuda(v, "model_output")
+    _require_cuda(x, "latents")
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    vd = _dtype_code(v, "model_output")
+    if v.shape != x.shape:
+        raise ValueError(f"mixgrpo_b200: model_output {tuple(v.shape)} and latents {tuple(x.shape)} differ")
+    v = v if v.is_contiguous() else v.contiguous()
+    B = v.shape[0]
+    n = v[0].numel()
+    dev = v.device
+    x, x_bs = _rows(x, "latents")
+    noise_p = in_p = m1_p = m2_p = None
+    in_bs = n
+    keep = [v, x]
+    if src == SRC_NOISE:
+        if noise is None:
+            raise ValueError("mixgrpo_b200: rollout step needs explicit `noise`")
+        _require_cuda(noise, "noise")
+        want = v.dtype if family == FLOW else torch.float32      # SU:193 vs SU:238 / SU:320
+        if noise.dtype != want or not noise.is_contiguous():
+            noise = noise.to(want).contiguous()
+        if noise.shape != v.shape:
+            raise ValueError("mixgrpo_b200: noise shape mismatch")
+        noise_p = noise.data_ptr()
+        keep.append(noise)
+    elif src == SRC_GIVEN:
+        _require_cuda(x_next, "prev_sample")
+        if x_next.dtype != torch.float32:
+            x_next = x_next.to(torch.float32)
+        if x_next.shape != v.shape:
+            raise ValueError("mixgrpo_b200: prev_sample shape mismatch")
+        x_next, in_bs = _rows(x_next, "prev_sample")
+        in_p = x_next.data_ptr()
+        keep.append(x_next)
+    if family == DPM and order >= 2:
+        m1 = m1.contiguous()
+        m1_p = m1.data_ptr()
+        keep.append(m1)
+        if order == 3:
+            m2 = m2.contiguous()
+            m2_p = m2.data_ptr()
+            keep.append(m2)
+
+    out = None
+    out_p, out_bs = None, n
+    if src != SRC_GIVEN:
+        if out_x_next is None:
+            out = torch.empty(v.shape, dtype=torch.float32, device=dev)
+            out_p = out.data_ptr()
+        else:
+            if out_x_next.dtype != torch.float32 or out_x_next.shape != v.shape or not out_x_next[0].is_contiguous():
+                raise ValueError("mixgrpo_b200: out_x_next must be fp32, same shape, contiguous per sample")
+            out = out_x_next
+            out_p, out_bs = out.data_ptr(), (out.stride(0) if B > 1 else n)
+    x0 = torch.empty(v.shape, dtype=torch.float32, device=dev) if want_x0 else None
+    mean = torch.empty(v.shape, dtype=torch.float32, device=dev) if want_mean else None
+    logp = None
+    if want_logp:
+        if out_logp is not None:
+            if out_logp.dtype != torch.float32 or out_logp.numel() != B or not out_logp.is_contiguous():
+                raise ValueError("mixgrpo_b200: out_logp must be a contiguous fp32 [B] tensor")
+            logp = out_logp
+        else:
+            logp = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, B, n) if want_logp else None
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    st = _stream_ptr(dev)
+    common_out = (out_p, out_bs, x0.data_ptr() if want_x0 else None, mean.data_ptr() if want_mean else None,
+                  logp.data_ptr() if want_logp else None, ws.data_ptr() if want_logp else None,
+                  ws.numel() if want_logp else 0, B, n, C.byref(coefs))
+    with torch.cuda.device(dev):
+        if family == FLOW:
+            rc = lib.mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src, flags, st)
+        elif family == DANCE:
+            rc = lib.mixgrpo_dance_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src,
+                                        1 if sde_solver else 0, flags, st)
+        elif family == DPM:
+            rc = lib.mixgrpo_dpm_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, m1_p, m2_p, order, *common_out, src, flags, st)
+        else:
+            raise ValueError(family)
+    _cabi.check(rc, ("flow_step", "dance_step", "dpm_step")[family])
+    launch_count += 1
+    del keep
+    return (x_next if src == SRC_GIVEN else out), x0, logp, mean
+
+
+def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, grad_logp: torch.Tensor,
+                     coefs: StepCoefs, round_like_torch: bool = False) -> torch.Tensor:
+    """grad of sum_b grad_logp[b]*logp[b] w.r.t. model_output; dtype = model_output.dtype."""
+    global launch_count
+    lib = _cabi.lib()
+    for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (grad_logp, "grad_log_prob")):
+        _require_cuda(t, nm)
+    vd = _dtype_code(v, "model_output")
+    v = v if v.is_contiguous() else v.contiguous()
+    B, n = v.shape[0], v[0].numel()
+    x, x_bs = _rows(x.to(torch.float32), "latents")
+    x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
+    g = grad_logp.to(torch.float32).contiguous()
+    if g.numel() != B:
+        raise ValueError("mixgrpo_b200: grad_log_prob must have one entry per sample")
+    grad_v = torch.empty_like(v)
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    with torch.cuda.device(v.device):
+        rc = lib.mixgrpo_logprob_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, g.data_ptr(),
+                                     grad_v.data_ptr(), B, n, C.byref(coefs), flags, _stream_ptr(v.device))
+    _cabi.check(rc, "logprob_bwd")
+    launch_count += 1
+    return grad_v
+
+
+def group_advantages(rewards: torch.Tensor, weights: Optional[torch.Tensor], num_generations: int, trim_size: int = 0,
+                     use_group: bool = True, stat_rewards: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rewards [n_models, local_B] fp32 -> advantages [local_B] fp32 (TR:439-501)."""
+    global launch_count
+    lib = _cabi.lib()
+    _require_cuda(rewards, "rewards")
+    r = rewards.to(torch.float32)
+    if r.dim() == 1:
+        r = r.unsqueeze(0)
+    r = r.contiguous()
+    n_models, local_B = r.shape
+    w_p = None
+    if weights is not None:
+        weights = weights.to(device=r.device, dtype=torch.float32).contiguous()
+        if weights.numel() != n_models:
+            raise ValueError("mixgrpo_b200: one weight per reward model required")
+        w_p = weights.data_ptr()
+    s_p, n_stat = None, 0
+    if stat_rewards is not None:
+        stat_rewards = stat_rewards.to(device=r.device, dtype=torch.float32).contiguous()
+        s_p, n_stat = stat_rewards.data_ptr(), stat_rewards.numel()
+    adv = torch.zeros((local_B,), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        rc = lib.mixgrpo_group_advantages(r.data_ptr(), w_p, n_models, local_B, int(num_generations), int(trim_size),
+                                          1 if use_group else 0, s_p, n_stat, adv.data_ptr(), _stream_ptr(r.device))
+    _cabi.check(rc, "group_advantages")
+    launch_count += 1
+    return adv
+
+
+def grpo_loss_fwd_bwd(new_logp: torch.Tensor, old_logp: torch.Tensor, advantages: torch.Tensor, clip_range: float,
+                      adv_clip_max: float, kl_coeff: float, denom: float, want_grad: bool = True,
+                      stats_accum: Optional[torch.Tensor] = None):
+    """Returns (stats[4] = loss, policy, kl, clip_frac ; grad_new_logp or None).  TR:560-583."""
+    global launch_count
+    lib = _cabi.lib()
+    for t, nm in ((new_logp, "new_log_probs"), (old_logp, "old_log_probs"), (advantages, "advantages")):
+        _require_cuda(t, nm)
+    nl = new_logp.detach().to(torch.float32).contiguous().view(-1)
+    ol = old_logp.detach().to(torch.float32).contiguous().view(-1)
+    ad = advantages.detach().to(torch.float32).contiguous().view(-1)
+    B = nl.numel()
+    if ol.numel() != B or ad.numel() != B:
+        raise ValueError("mixgrpo_b200: new/old log-probs and advantages must have the same length")
+    stats = torch.empty((4,), dtype=torch.float32, device=nl.device)
+    grad = torch.empty((B,), dtype=torch.float32, device=nl.device) if want_grad else None
+    acc_p = None
+    if stats_accum is not None:
+        if stats_accum.dtype != torch.float32 or stats_accum.numel() != 4 or not stats_accum.is_contiguous():
+            raise ValueError("mixgrpo_b200: stats_accum must be a contiguous fp32 [4] tensor")
+        acc_p = stats_accum.data_ptr()
+    with torch.cuda.device(nl.device):
+        rc = lib.mixgrpo_grpo_loss(nl.data_ptr(), ol.data_ptr(), ad.data_ptr(), B, float(clip_range), float(adv_clip_max),
+                                   float(kl_coeff), float(denom), stats.data_ptr(), grad.data_ptr() if want_grad else None,
+                                   acc_p, _stream_ptr(nl.device))
+    _cabi.check(rc, "grpo_loss")
+    launch_count += 1
+    return stats, grad
+
+
+def pack_latents(latents: torch.Tensor, batch_size: int, num_channels: int, height: int, width: int) -> torch.Tensor:
+    """(B,C,H,W) -> (B,(H/2)(W/2),4C), TR:94-99."""
+    global launch_count
+    _require_cuda(latents, "latents")
+    code = _dtype_code(latents, "latents")
+    src = latents.contiguous().view(batch_size, num_channels, height, width)
+    dst = torch.empty((batch_size, (height // 2) * (width // 2), num_channels * 4), dtype=latents.dtype, device=latents.device)
+    with torch.cuda.device(latents.device):
+        rc = _cabi.lib().mixgrpo_pack_latents(src.data_ptr(), dst.data_ptr(), code, batch_size, num_channels, height, width,
+                                              _stream_ptr(latents.device))
+    _cabi.check(rc, "pack_latents")
+    launch_count += 1
+    return dst
+
+
+def unpack_latents(latents: torch.Tensor, height: int, width: int, vae_scale_factor: int, divisor: float = 1.0,
+                   shift: float = 0.0) -> torch.Tensor:
+    """(B,S,4C) -> (B,C,H',W') with H' = 2*(height // (2*vae_scale_factor)), TR:102-115; optional fused
+    ``x / divisor + shift`` (TR:287)."""
+    global launch_count
+    _require_cuda(latents, "latents")
+    code = _dtype_code(latents, "latents")
+    b, _, ch = latents.shape
+    hh = 2 * (int(height) // (vae_scale_factor * 2))
+    ww = 2 * (int(width) // (vae_scale_factor * 2))
+    src = latents.contiguous()
+    dst = torch.empty((b, ch // 4, hh, ww), dtype=latents.dtype, device=latents.device)
+    with torch.cuda.device(latents.device):
+        rc = _cabi.lib().mixgrpo_unpack_latents(src.data_ptr(), dst.data_ptr(), code, b, ch // 4, hh, ww, float(divisor),
+                                                float(shift), _stream_ptr(latents.device))
+    _cabi.check(rc, "unpack_latents")
+    launch_count += 1
+    return dst

@@ -1,0 +1,196 @@
+"""B200-native rollout and policy-update drivers built on the fused kernels.
+
+The reference rolls a prompt group out as 12 sequential batch-1 loops (TR:213,231; TR =
+/root/reference/fastvideo/train_grpo_flux.py) and updates the policy one (sample, window step) at a time
+with ~15 scalar kernels, 4 all-reduces and 5 ``.item()`` syncs each (TR:536-600).  Here:
+
+* ``rollout``            — the whole group in ONE batch: per step one model call + one fused kernel that
+                           reads ``all_latents[:, i]`` and writes ``all_latents[:, i+1]`` in place.
+* ``make_samples``       — TR:400-415 (views, no copies).
+* ``policy_update``      — log-prob forward → loss fwd+bwd → log-prob backward: three launches, zero host
+                           syncs; returns ``grad_model_output`` for ``pred.backward(grad)``.
+* ``balance_pos_neg`` / ``shuffle_timesteps`` — sample bookkeeping of TR:503-532 and
+                           fastvideo/models/reward_model/utils.py:18-48.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import coefs as _coefs
+from . import grpo as _grpo
+from . import ops as _ops
+from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+from .sampling_utils import DPMState, _dpm_order, _flash_schedule, _mode
+
+
+@dataclass
+class SamplerConfig:
+    """The ``args`` fields the reference's operators read (SU:29-152, TR:145-180); defaults are the
+    shipped MixGRPO configuration (scripts/finetune/finetune_flux_grpo_MixGRPO.sh:48-79)."""
+    sampling_steps: int = 25
+    eta: float = 0.7
+    shift: float = 3.0
+    flow_grpo_sampling: bool = True
+    dpm_algorithm_type: str = "null"          # "null" | "dpmsolver" | "dpmsolver++"
+    dpm_apply_strategy: str = "post"          # "post" | "all"
+    dpm_post_compress_ratio: float = 0.4
+    dpm_solver_order: int = 2
+    dpm_solver_type: str = "midpoint"
+    sample_strategy: str = "progressive"
+    drop_last_sample: bool = False
+    rounding: str = "auto"
+
+
+def sigma_schedule(sampling_steps: int, shift: float, device=None) -> torch.Tensor:
+    """TR:200-202: ``sd3_time_shift(shift, linspace(1, 0, N+1))``."""
+    t = torch.linspace(1, 0, sampling_steps + 1)
+    if device is not None:
+        t = t.to(device)
+    return (shift * t) / (1 + (shift - 1) * t)
+
+
+def window_mask(sampling_steps: int, timesteps_train: Sequence[int], training_strategy: str = "part") -> List[bool]:
+    """TR:251-256: ``determistic[i]`` is False exactly on the SDE-window steps."""
+    if training_strategy == "all":
+        return [False] * sampling_steps
+    det = [True] * sampling_steps
+    for i in timesteps_train:
+        det[i] = False
+    return det
+
+
+def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.Tensor, sigmas: torch.Tensor,
+            determistic: Sequence[bool], cfg: SamplerConfig, noises: Optional[Sequence[Optional[torch.Tensor]]] = None,
+            want_x0: bool = False):
+    """Batched equivalent of SU:61-155.  ``model(latents, sigma_float, step) -> model_output`` stands for the
+    DiT forward (SU:62-82).  Returns ``(z_final, latents, all_latents (B,N+1,...), all_log_probs (B,N), sigmas)``
+    where ``sigmas`` is the schedule actually used (rebuilt in Flash "post" mode, SU:33-54)."""
+    mode = _mode(cfg.rounding)
+    dpm_state = None
+    last_sde = None
+    flash = False
+    if "dpmsolver" in cfg.dpm_algorithm_type:
+        dpm_state = DPMState(order=cfg.dpm_solver_order)
+        if cfg.dpm_apply_strategy == "post":
+            assert cfg.sample_strategy == "progressive", "post strategy is only supported for progressive sampling"
+            sigmas, last_sde = _flash_schedule(cfg, sigmas, determistic)
+            flash = True
+    n_steps = sigmas.size(0) - 1
+    B, dev = z.shape[0], z.device
+    traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
+    traj[:, 0].copy_(z)
+    logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
+    host_sig = _coefs.host_schedule(sigmas).tolist()
+    x0 = None
+    need_x0_last = cfg.drop_last_sample or want_x0
+    for i in range(n_steps):
+        x, out = traj[:, i], traj[:, i + 1]
+        v = model(z if i == 0 else x, host_sig[i], i)
+        bf16_v = v.dtype == torch.bfloat16
+        rnd = bf16_v and mode != "fp32"
+        nz = noises[i] if noises is not None else None
+        use_dpm = dpm_state is not None and (cfg.dpm_apply_strategy == "all" or (flash and i > last_sde))
+        # x0 is only materialised when something downstream reads it: the DPM history, or the caller
+        keep_x0 = (dpm_state is not None) or (need_x0_last and i == n_steps - 1)
+        if use_dpm:
+            sde = (not determistic[i]) if cfg.dpm_apply_strategy == "all" else False
+            order = _dpm_order(cfg, i, n_steps, dpm_state)
+            m1 = dpm_state.model_outputs[-1] if order >= 2 else None
+            m2 = dpm_state.model_outputs[-2] if order == 3 else None
+            k, _ = _coefs.dpm(sigmas, i, order, cfg.dpm_algorithm_type, cfg.dpm_solver_type, mode, bf16_v)
+            if sde and nz is None:
+                nz = torch.randn(v.shape, device=dev, dtype=torch.float32)
+            _, x0, _, _ = _ops.fused_step(_ops.DPM, v, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
+                                          noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
+                                          out_logp=logps_t[i], want_x0=True, round_like_torch=rnd)
+            dpm_state.update(x0)
+            dpm_state.update_lower_order()
+        else:
+            fam = _ops.FLOW if cfg.flow_grpo_sampling else _ops.DANCE
+            k, _ = (_coefs.flow if cfg.flow_grpo_sampling else _coefs.dance)(sigmas, i, cfg.eta, mode, bf16_v)
+            if determistic[i]:
+                src, nz = SRC_DETERMINISTIC, None
+            else:
+                src = SRC_NOISE
+                if nz is None:
+                    nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32)
+            _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, sde_solver=not determistic[i], out_x_next=out,
+                                          out_logp=logps_t[i], want_x0=keep_x0, round_like_torch=rnd)
+            if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
+                dpm_state.update(x0)
+                dpm_state.update_lower_order()
+    z_final = traj[:, n_steps]
+    latents = x0 if cfg.drop_last_sample else z_final                        # SU:149-152
+    return z_final, latents, traj, logps_t.t(), sigmas
+
+
+def make_samples(all_latents: torch.Tensor, all_log_probs: torch.Tensor, sigmas: torch.Tensor, sampling_steps: int) -> Dict:
+    """TR:400-415: the last transition is never trained, so N-1 transitions remain (views only)."""
+    B = all_latents.shape[0]
+    host = _coefs.host_schedule(sigmas).tolist()
+    tvals = [int(s * 1000) for s in host][:sampling_steps]                   # TR:401
+    timesteps = torch.tensor([tvals] * B, dtype=torch.long).to(all_latents.device, non_blocking=True)
+    return {
+        "timesteps": timesteps[:, :-1],
+        "latents": all_latents[:, :-1][:, :-1],
+        "next_latents": all_latents[:, 1:][:, :-1],
+        "log_probs": all_log_probs[:, :-1],
+    }
+
+
+def shuffle_timesteps(samples: Dict, generator: Optional[torch.Generator] = None):
+    """TR:503-509 (training_strategy == "all"): independent random step order per sample.  Returns perms."""
+    B, T = samples["timesteps"].shape
+    dev = samples["timesteps"].device
+    perms = torch.stack([torch.randperm(T, generator=generator) for _ in range(B)]).to(dev)
+    rows = torch.arange(B, device=dev)[:, None]
+    for key in ("timesteps", "latents", "next_latents", "log_probs"):
+        samples[key] = samples[key][rows, perms]
+    return perms
+
+
+def balance_pos_neg(samples: List[dict], use_random: bool = False, rng: Optional[random.Random] = None) -> List[dict]:
+    """fastvideo/models/reward_model/utils.py:18-48 — interleave positive- and negative-advantage samples.
+    Samples with advantage exactly 0 are dropped, like the reference.  ``rng`` defaults to the global
+    ``random`` module the reference uses."""
+    rng = rng or random
+    if use_random:
+        return rng.sample(samples, len(samples))
+    signs = [float(s["advantages"]) if not torch.is_tensor(s["advantages"]) else s["advantages"].item() for s in samples]
+    pos = [s for s, a in zip(samples, signs) if a > 0]
+    neg = [s for s, a in zip(samples, signs) if a < 0]
+    pos = rng.sample(pos, len(pos))
+    neg = rng.sample(neg, len(neg))
+    small, large = (pos, neg) if len(pos) < len(neg) else (neg, pos)
+    mixed = []
+    for a, b in zip(small, large):
+        mixed += [a, b]
+    mixed.extend(large[len(small):])
+    return mixed
+
+
+def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Tensor, old_log_probs: torch.Tensor,
+                  advantages: torch.Tensor, sigmas: torch.Tensor, index: int, cfg: SamplerConfig, *, clip_range: float,
+                  adv_clip_max: float, kl_coeff: float, gradient_accumulation_steps: int, num_train_timesteps: int,
+                  stats_accum: Optional[torch.Tensor] = None):
+    """One (samples, window step) policy update, TR:542-585 without autograd: given the model output ``v`` for
+    the stored ``latents`` it returns ``(stats[4], new_log_probs [B], grad_v)`` where ``grad_v`` is
+    dloss/dv — hand it to ``v.backward(grad_v)`` to continue into the DiT.  Three kernel launches, no sync."""
+    mode = _mode(cfg.rounding)
+    bf16_v = v.dtype == torch.bfloat16
+    rnd = bf16_v and mode != "fp32"
+    if cfg.flow_grpo_sampling:
+        fam, (k, _) = _ops.FLOW, _coefs.flow(sigmas, index, cfg.eta, mode, bf16_v)
+    else:
+        fam, (k, _) = _ops.DANCE, _coefs.dance(sigmas, index, cfg.eta, mode, bf16_v)
+    vd = v.detach()
+    _, _, new_lp, _ = _ops.fused_step(fam, vd, latents, k, src=SRC_GIVEN, x_next=next_latents, want_x0=False,
+                                      sde_solver=True, round_like_torch=rnd)
+    stats, g_lp = _grpo.grpo_loss_and_grad(new_lp, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
+                                           gradient_accumulation_steps, num_train_timesteps, stats_accum=stats_accum)
+    grad_v = _ops.logprob_backward(fam, vd, latents, next_latents, g_lp, k, rnd)
+    return stats, new_lp, grad_v

