@@ -79,10 +79,10 @@ typedef struct mixgrpo_step_coefs {
   float c[16];
 } mixgrpo_step_coefs;
 
-/* Bytes of zero-initialised device workspace the step kernels need for (B, n).  The block holds the
- * per-sample arrival counters and the per-CTA partial sums of the deterministic log-prob reduction;
- * kernels leave the counters zeroed again, so one allocation can be reused by successive launches
- * on the same stream. */
+/* Bytes of zero-initialised device workspace the step kernels need for (B, n): one 64-bit packed
+ * accumulator per sample ([fixed-point sum | poison | arrival count], csrc/step_kernels.cu) for the
+ * deterministic log-prob reduction.  Kernels leave the words zeroed again, so one allocation can be
+ * reused by successive launches on the same stream. */
 int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
 
 /* ABI / build introspection. */

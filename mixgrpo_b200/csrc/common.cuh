@@ -20,7 +20,6 @@ namespace mg {
 
 constexpr int kThreads = 256;   // threads per CTA for the streaming kernels
 constexpr int kVec = 8;         // latent scalars owned by one thread per tile
-constexpr int kMaxPartials = 4096;
 
 // ---------------------------------------------------------------- 256/128-bit streaming access
 __device__ __forceinline__ void ld_stream(const float* p, float (&r)[8]) {
@@ -108,7 +107,5 @@ __device__ __forceinline__ float block_sum(float v, float* s_warp /* [kThreads/3
   return t;
 }
 
-// workspace layout: [B uint32 counters, padded to 256 B][B * nblk float partials]
-__host__ __device__ inline int64_t ws_counter_bytes(int64_t B) { return ((B * 4 + 255) / 256) * 256; }
 
 }  // namespace mg

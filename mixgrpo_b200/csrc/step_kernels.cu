@@ -2,21 +2,20 @@
 // of the reference: flow_grpo_step (SU:157-210), dance_grpo_step (SU:212-253) and dpm_step with its
 // order-1/2/3 updates (SU:273-639).  SU = /root/reference/fastvideo/utils/sampling_utils.py.
 //
-// Data layout: every tensor is (B, n) with n = S*64 packed-latent scalars; thread t of CTA (bx, b)
-// owns scalars [8*(tile*256+t), +8) of sample b in EVERY stream, so v (bf16, 16 B), x / noise /
-// history / outputs (fp32, 32 B) are each a single LDG.128 / LDG.256 / STG.256 per thread and a
-// warp request covers whole 128-B lines.  All loads of the UNROLL tiles a CTA owns are issued before
-// any math (memory-level parallelism), results are stored straight from registers; nothing is
-// staged in shared memory because no byte is touched twice.
+// Data layout: every tensor is (B, n) with n = S*64 packed-latent scalars; thread t of a CTA owns
+// scalars [8t, 8t+8) of the CTA's 2048-scalar tile in EVERY stream, so v (bf16, 16 B), x / noise /
+// history / outputs (fp32, 32 B) are each a single LDG.128 / LDG.256 / STG.256 per thread and a warp
+// request covers whole 128-B lines with every sector used.  Results are stored straight from registers;
+// nothing is staged in shared memory because no byte is touched twice.
 //
 // Arithmetic: every product/sum the reference performs as a separate torch kernel is performed here
 // with __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn (no FMA contraction) in the same order, and with the
 // same bf16 rounding points when MIXGRPO_FLAG_ROUND_LIKE_TORCH is set, so x_next / x0 / mean are
 // bit-identical to the reference on identical inputs.  Only the log-prob reduction order differs.
 //
-// log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> CTA -> partials[b][bx]; the last CTA
-// of a sample (arrival counter) adds the partials in index order, so the result does not depend on
-// CTA scheduling, and resets the counter (graph-replay safe).
+// log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> CTA -> ONE packed fixed-point atomicAdd per
+// CTA (count + sum in a 64-bit word): order-independent, hence bitwise reproducible; the last arriver
+// writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below.
 #include "common.cuh"
 
 namespace mg {
@@ -34,19 +33,18 @@ struct StepParams {
   float* x0_out;
   float* mean_out;
   float* logp_out;
-  float* partials;
-  unsigned* counters;
+  unsigned long long* acc;
   long long n, x_bs, in_bs, out_bs;
-  int nblk;
+  int B, tiles;
   mixgrpo_step_coefs k;
 };
 
 // ------------------------------------------------------------------ per-tile arithmetic
 // FAM/SRC/ORDER/RND/SDE are compile-time so each instantiation is straight-line code.
 template <int FAM, int SRC, int ORDER, bool RND, bool SDE, int N>
-__device__ __forceinline__ float tile_math(const mixgrpo_step_coefs& k, const float (&v)[N], const float (&x)[N],
+__device__ __forceinline__ void tile_math(const mixgrpo_step_coefs& k, const float (&v)[N], const float (&x)[N],
                                            const float (&a)[N], const float (&m1)[N], const float (&m2)[N],
-                                           float (&xn)[N], float (&x0)[N], float (&mu)[N]) {
+                                           float (&xn)[N], float (&x0)[N], float (&mu)[N], float (&dd)[N]) {
   const float* c = k.c;
   float t[N];
   // x0 = x - sigma*v          (SU:175, SU:226, SU:394)
@@ -140,107 +138,166 @@ __device__ __forceinline__ float tile_math(const mixgrpo_step_coefs& k, const fl
     for (int i = 0; i < N; ++i) xn[i] = a[i];
   }
   // squared residual of the transition (SU:202, SU:245, SU:377)
-  float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    float d = __fsub_rn(xn[i], mu[i]);
-    acc = fmaf(d, d, acc);
+    const float d = __fsub_rn(xn[i], mu[i]);
+    dd[i] = d * d;
   }
-  return acc;
 }
 
 // ------------------------------------------------------------------ the streaming kernel
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, int VEC, int UNROLL>
-__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepParams p) {
-  __shared__ float s_warp[kThreads / 32];
-  __shared__ int s_last;
+// Grid (ctas_per_sample, B); CTA = 256 threads; a CTA-tile is 2048 consecutive scalars of one sample and
+// thread t owns scalars [8t, 8t+8) of it in every stream (one LDG.128 for bf16, one LDG.256 for fp32, one
+// STG.256 per output).  Measured on B200 (tools/ubench.cu, profiles/r01_design_space.md): what matters for
+// this 50-100 MB pass is bytes in flight — all of a thread's loads are issued before any math, the math
+// is done pair-wise so the kernel stays at <= 40 registers (6 CTAs = 1536 threads per SM), and CTAs retire
+// without waiting on anything (a persistent / software-pipelined variant and every fence+ticket
+// reduction were 20-30 % slower).
+//
+// log-prob reduction — one atomic per CTA, deterministic, no fence:
+//   acc[b] is a 64-bit word  [ sum : 40 bit fixed point Q8.32 | poison : 12 | arrivals : 12 ].
+//   A CTA adds  (1, poison?, round(r * 2^32))  with r = sum_cta(d^2) / (n * 2 s^2)  in ONE atomicAdd.
+//   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in; the CTA
+//   whose returned count is the last one owns the complete sum in (old + mine), writes
+//   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
+//   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2); a contribution that is not finite
+//   or would overflow the field (mean squared normalised residual > 510) poisons the sample -> NaN.
+constexpr int kTile = kThreads * kVec;          // scalars per CTA-tile
+constexpr int kCountBits = 12, kPoisonBits = 12;
+constexpr int kMaxCtasPerSample = (1 << kCountBits) - 1;
+
+template <class T, bool VECTOR>
+__device__ __forceinline__ void load_tile(const T* base, long long off, long long n, float (&r)[kVec]) {
+  if constexpr (VECTOR) {
+    ld_stream(base + off + threadIdx.x * kVec, r);          // caller guarantees off + 8t < n
+  } else {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const long long i = off + j * kThreads + threadIdx.x;
+      float one[1] = {0.f};
+      if (i < n) ld_stream(base + i, one);
+      r[j] = one[0];
+    }
+  }
+}
+
+template <bool VECTOR>
+__device__ __forceinline__ void store_tile(float* base, long long off, long long n, const float (&r)[kVec]) {
+  if constexpr (VECTOR) {
+    st_stream(base + off + threadIdx.x * kVec, r);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const long long i = off + j * kThreads + threadIdx.x;
+      if (i < n) base[i] = r[j];
+    }
+  }
+}
+
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
+__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || WMEAN || !VECTOR || (FAM == kDance && SDE)) ? 4 : 6)
+step_kernel(const __grid_constant__ StepParams p) {
   const int b = blockIdx.y;
   const long long n = p.n;
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
   const float* xp = p.x + (long long)b * p.x_bs;
-  const NT* np = reinterpret_cast<const NT*>(p.noise) + (long long)b * n;
-  const float* ip = p.x_in + (long long)b * p.in_bs;
-  const float* m1p = p.m1 + (long long)b * n;
-  const float* m2p = p.m2 + (long long)b * n;
-
-  float v[UNROLL][VEC], x[UNROLL][VEC], a[UNROLL][VEC], m1[UNROLL][VEC], m2[UNROLL][VEC];
-  long long idx[UNROLL];
-#pragma unroll
-  for (int u = 0; u < UNROLL; ++u) {
-    idx[u] = (((long long)blockIdx.x * UNROLL + u) * kThreads + threadIdx.x) * VEC;
-    if (idx[u] < n) {
-      ld_stream(vp + idx[u], v[u]);
-      ld_stream(xp + idx[u], x[u]);
-      if constexpr (SRC == MIXGRPO_SRC_NOISE) ld_stream(np + idx[u], a[u]);
-      if constexpr (SRC == MIXGRPO_SRC_GIVEN) ld_stream(ip + idx[u], a[u]);
-      if constexpr (FAM == kDpm && ORDER >= 2) ld_stream(m1p + idx[u], m1[u]);
-      if constexpr (FAM == kDpm && ORDER == 3) ld_stream(m2p + idx[u], m2[u]);
-    }
-  }
   float acc = 0.f;
+
+  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+    const long long off = (long long)tile * kTile;
+    // vector path: n % 8 == 0, so a thread's 8 scalars are all inside or all outside the sample
+    if (VECTOR && off + threadIdx.x * kVec >= n) continue;
+    float v[kVec], x[kVec], a[kVec], m1[kVec], m2[kVec];
+    load_tile<VT, VECTOR>(vp, off, n, v);
+    load_tile<float, VECTOR>(xp, off, n, x);
+    if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
+    if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR>(p.x_in + (long long)b * p.in_bs, off, n, a);
+    if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
+    if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
+
+    float xn[kVec], x0[kVec], mu[WMEAN ? kVec : 2];
 #pragma unroll
-  for (int u = 0; u < UNROLL; ++u) {
-    if (idx[u] < n) {
-      float xn[VEC], x0[VEC], mu[VEC];
-      acc += tile_math<FAM, SRC, ORDER, RND, SDE>(p.k, v[u], x[u], a[u], m1[u], m2[u], xn, x0, mu);
-      if constexpr (SRC != MIXGRPO_SRC_GIVEN) {
-        if (p.x_out) st_stream(p.x_out + (long long)b * p.out_bs + idx[u], xn);
+    for (int j = 0; j < kVec; j += 2) {           // pair-wise: short live ranges, packed bf16 rounding
+      const float v2[2] = {v[j], v[j + 1]}, x2[2] = {x[j], x[j + 1]}, a2[2] = {a[j], a[j + 1]};
+      const float m12[2] = {m1[j], m1[j + 1]}, m22[2] = {m2[j], m2[j + 1]};
+      float xn2[2], x02[2], mu2[2], dd2[2];
+      tile_math<FAM, SRC, ORDER, RND, SDE>(p.k, v2, x2, a2, m12, m22, xn2, x02, mu2, dd2);
+      xn[j] = xn2[0]; xn[j + 1] = xn2[1];
+      x0[j] = x02[0]; x0[j + 1] = x02[1];
+      if constexpr (WMEAN) { mu[j] = mu2[0]; mu[j + 1] = mu2[1]; }
+      if constexpr (VECTOR) {
+        acc += dd2[0] + dd2[1];
+      } else {                                    // ragged tail: mask scalars beyond the sample
+        if (off + j * kThreads + threadIdx.x < n) acc += dd2[0];
+        if (off + (j + 1) * kThreads + threadIdx.x < n) acc += dd2[1];
       }
-      if (p.x0_out) st_stream(p.x0_out + (long long)b * n + idx[u], x0);
-      if (p.mean_out) st_stream(p.mean_out + (long long)b * n + idx[u], mu);
     }
+    if constexpr (SRC != MIXGRPO_SRC_GIVEN) {
+      if (p.x_out) store_tile<VECTOR>(p.x_out + (long long)b * p.out_bs, off, n, xn);
+    }
+    if (p.x0_out) store_tile<VECTOR>(p.x0_out + (long long)b * n, off, n, x0);
+    if constexpr (WMEAN) store_tile<VECTOR>(p.mean_out + (long long)b * n, off, n, mu);
   }
   if (p.logp_out == nullptr) return;
 
-  // deterministic cross-CTA finish
-  const float bsum = block_sum(acc, s_warp);
-  const int nblk = p.nblk;
-  if (threadIdx.x == 0) {
-    p.partials[(long long)b * nblk + blockIdx.x] = bsum;
-    __threadfence();
-    const unsigned ticket = atomicAdd(&p.counters[b], 1u);
-    s_last = (ticket == (unsigned)(nblk - 1));
-  }
+  __shared__ float s_warp[kThreads / 32];
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = acc;
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < nblk; i += kThreads) s += __ldcg(&p.partials[(long long)b * nblk + i]);
-    const float tot = block_sum(s, s_warp);
-    if (threadIdx.x == 0) {
-      const float msq = __fdiv_rn(tot, (float)n);
+  if (warp != 0) return;                           // warps 1..7 are done: nothing waits on the atomic
+  float t = lane < kThreads / 32 ? s_warp[lane] : 0.f;
+  t = warp_sum(t);
+  if (lane == 0) {
+    const int ctas = gridDim.x;
+    float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
+    const float cap = 255.0f / (float)ctas;
+    unsigned long long add = 1ull;
+    if (!(r >= 0.f && r <= cap)) {                 // NaN, inf, negative (two_var < 0) or would overflow
+      add += 1ull << kCountBits;
+      r = 0.f;
+    }
+    add += __float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits);
+    const unsigned long long old = atomicAdd(&p.acc[b], add);
+    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
+      const unsigned long long tot = old + add;
+      float q = (float)((double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0));
+      if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) q = __int_as_float(0x7fc00000);
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
-      p.logp_out[b] = __fsub_rn(__fsub_rn(__fdiv_rn(-msq, p.k.two_var), p.k.log_scale), p.k.log_norm);
-      p.counters[b] = 0u;
+      p.logp_out[b] = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
+      p.acc[b] = 0ull;
     }
   }
 }
 
 // ------------------------------------------------------------------ host-side dispatch
-static int g_unroll = 2;   // tiles per CTA on the vector path (bench knob, mixgrpo_set_tuning key 0)
+static int g_max_ctas_per_sample = kMaxCtasPerSample;   // bench knob (mixgrpo_set_tuning key 0)
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, int VEC, int UNROLL>
-static int launch(StepParams& p, int64_t B, cudaStream_t st) {
-  const long long per_cta = (long long)kThreads * VEC * UNROLL;
-  p.nblk = (int)((p.n + per_cta - 1) / per_cta);
-  dim3 grid((unsigned)p.nblk, (unsigned)B);
-  step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VEC, UNROLL><<<grid, kThreads, 0, st>>>(p);
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
+static int launch(StepParams& p, cudaStream_t st) {
+  p.tiles = (int)((p.n + kTile - 1) / kTile);
+  int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
+  dim3 grid((unsigned)ctas, (unsigned)p.B);
+  step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, WMEAN><<<grid, kThreads, 0, st>>>(p);
   return (int)cudaGetLastError();
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE>
-static int pick_width(StepParams& p, int64_t B, bool vec_ok, cudaStream_t st) {
-  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, 1, 4>(p, B, st);
-  if constexpr (FAM == kFlow) {
-    switch (g_unroll) {
-      case 1: return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, kVec, 1>(p, B, st);
-      case 4: return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, kVec, 4>(p, B, st);
-      default: break;
+static int pick_width(StepParams& p, int64_t, bool vec_ok, cudaStream_t st) {
+  if constexpr (FAM == kDpm) {                     // dpm_step never returns the mean (SU:385)
+    if (p.mean_out) return MIXGRPO_EINVAL;
+    if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, false>(p, st);
+    return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, false>(p, st);
+  } else {
+    if (p.mean_out) {
+      if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, true>(p, st);
+      return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, true>(p, st);
     }
+    if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, false>(p, st);
+    return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, false>(p, st);
   }
-  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, kVec, 2>(p, B, st);
 }
 
 template <int FAM, class VT, class NT, int ORDER, bool RND, bool SDE>
@@ -257,7 +314,9 @@ static int pick_src(StepParams& p, int64_t B, int src, bool vec_ok, cudaStream_t
 
 static bool check_common(const void* v, const float* x, int64_t B, int64_t n, int v_dtype, void* ws, int64_t ws_bytes,
                          float* logp, int* err) {
-  if (!v || !x || B <= 0 || n <= 0 || B > 65535 || (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16)) {
+  // grid.y carries the sample index; tile indices are 32-bit inside the kernel
+  if (!v || !x || B <= 0 || B > 65535 || n <= 0 || (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) ||
+      (n + kTile - 1) / kTile >= 2147483647LL) {
     *err = MIXGRPO_EINVAL;
     return false;
   }
@@ -273,9 +332,9 @@ static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, con
                  float* mean_out, float* logp_out, void* ws, int64_t B, int64_t n, const mixgrpo_step_coefs* k) {
   p.v = v; p.x = x; p.noise = noise; p.x_in = x_in; p.m1 = m1; p.m2 = m2;
   p.x_out = x_out; p.x0_out = x0_out; p.mean_out = mean_out; p.logp_out = logp_out;
-  p.counters = reinterpret_cast<unsigned*>(ws);
-  p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ws_counter_bytes(B));
-  p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs; p.nblk = 0; p.k = *k;
+  p.acc = reinterpret_cast<unsigned long long*>(ws);
+  p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
+  p.B = (int)B; p.tiles = 0; p.k = *k;
 }
 
 // 256-bit path needs 32-B aligned fp32 streams, 16-B aligned bf16 streams and n, strides % 8 == 0.
@@ -293,18 +352,14 @@ using namespace mg;
 
 extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n) {
   if (B <= 0 || n <= 0) return 0;
-  const int64_t nblk_max = (n + 1023) / 1024;   // smallest CTA footprint (scalar path: 256 thr x 1 x 4)
-  return ws_counter_bytes(B) + B * nblk_max * (int64_t)sizeof(float);
+  return ((B * (int64_t)sizeof(unsigned long long) + 255) / 256) * 256;   // one packed accumulator per sample
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
-  if (key == 0) {
-    if (value != 1 && value != 2 && value != 4) return MIXGRPO_EINVAL;
-    int old = g_unroll;
-    g_unroll = value;
-    return old;
-  }
-  return MIXGRPO_EINVAL;
+  if (key != 0 || value < 1 || value > kMaxCtasPerSample) return MIXGRPO_EINVAL;
+  const int old = g_max_ctas_per_sample;
+  g_max_ctas_per_sample = value;
+  return old;
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs, const void* noise,

@@ -151,9 +151,9 @@ def dance_grpo_step(
     k, _std = _coefs.dance(sigmas, index, eta, mode, bf16_v)
     rnd = bf16_v and mode != "fp32"
     if not grpo:
-        _, x0, _, mean = _ops.fused_step(_ops.DANCE, model_output, latents, k, src=SRC_DETERMINISTIC, sde_solver=sde_solver,
+        mean, x0, _, _ = _ops.fused_step(_ops.DANCE, model_output, latents, k, src=SRC_DETERMINISTIC, sde_solver=sde_solver,
                                          want_mean=False, want_logp=False, round_like_torch=rnd)
-        return _, x0                                                  # x_next == mean on this path
+        return mean, x0                                               # x_next == mean on this path
     if prev_sample is None:
         if sde_solver:
             if noise is None:
@@ -240,6 +240,8 @@ def dpm_step(
         m1 = dpm_state.model_outputs[-1]
     if order == 3:
         m2 = dpm_state.model_outputs[-2]
+    if order == 3 and args.dpm_algorithm_type == "dpmsolver":
+        assert not sde_solver, "SDE solver is not supported for DPMSolver"          # SU:630
     k, _scale = _coefs.dpm(sigmas, step_index, order, args.dpm_algorithm_type, getattr(args, "dpm_solver_type", "midpoint"),
                            mode, bf16_v)
     if sde_solver:

@@ -140,13 +140,11 @@ def test_dpm_multistep_vs_oracle(algo, stype, order, dtype, sde):
         eps = eps.float()
         try:
             ref = O.dpm_step(v, x, idx, 25, SIG, algo=algo, solver_order=order, solver_type=stype, history=oh, noise=eps, sde_solver=sde)
-        except UnboundLocalError:
-            with pytest.raises(UnboundLocalError):
+        except (UnboundLocalError, AssertionError) as ref_err:
+            # dpmsolver order 3 is broken in the reference (SU:629-639); the drop-in fails the same way
+            with pytest.raises(type(ref_err)):
                 su.dpm_step(args, v.to(d), x.to(d), idx, SIG[:-1], SIG, dpm_state=st, variance_noise=eps.to(d), sde_solver=sde, rounding="ref_cpu")
             return
-        # feed both sides the ORACLE's history so one-ulp coefficient differences do not compound
-        for j, m in enumerate(oh.model_outputs[:-1]):
-            pass
         out = su.dpm_step(args, v.to(d), x.to(d), idx, SIG[:-1], SIG, dpm_state=st, variance_noise=eps.to(d), sde_solver=sde, rounding="ref_cpu")
         assert torch.equal(out[1].cpu(), ref[1]), f"x0 step {idx}"
         fin = torch.isfinite(ref[0])

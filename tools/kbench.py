@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--S", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=300)
     ap.add_argument("--sets", type=int, default=10)
-    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--profile", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, S, ns = a.B, a.S, a.sets
@@ -75,36 +75,46 @@ def main():
         print(json.dumps({"name": name, "B": B, "S": S, "us": round(us, 3), "GBps": round(gbs, 1), "bytes_per_elem": bytes_per_elem,
                           "frac_6533": round(gbs / 6533.5, 4), **kw}), flush=True)
 
+    if a.profile:
+        # short run for ncu: a few launches of the headline kernel and the train-path kernels
+        for i in range(6):
+            flow(i % ns, SRC_NOISE)
+        for i in range(3):
+            flow(i % ns, SRC_GIVEN, x0=False)
+            bwd(i % ns)
+        torch.cuda.synchronize()
+        print("profile run done")
+        return
+
+    def graph_time(fn):
+        nonlocal st
+        s = torch.cuda.Stream()
+        st_old = st
+        with torch.cuda.stream(s):
+            st = s.cuda_stream
+            fn(0)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                st = torch.cuda.current_stream().cuda_stream
+                for i in range(ns):
+                    fn(i)
+            st = st_old
+            us = timeit(lambda i: gr.replay(), 1, max(a.reps // ns, 10), warm=3) / ns
+        return us
+
     report("torch_copy_f32", timeit(copy, ns, a.reps), 8)
-    for unroll in (1, 2, 4):
-        lib.mixgrpo_set_tuning(0, unroll)
-        report("flow_sde_rollout_x0", timeit(lambda i: flow(i, SRC_NOISE), ns, a.reps), 16, unroll=unroll)
-        report("flow_sde_rollout_nox0", timeit(lambda i: flow(i, SRC_NOISE, x0=False), ns, a.reps), 12, unroll=unroll)
-        report("flow_ode_rollout_x0", timeit(lambda i: flow(i, SRC_DETERMINISTIC), ns, a.reps), 14, unroll=unroll)
-        report("flow_ode_rollout_nox0", timeit(lambda i: flow(i, SRC_DETERMINISTIC, x0=False), ns, a.reps), 10, unroll=unroll)
-        report("flow_train_fwd", timeit(lambda i: flow(i, SRC_GIVEN, x0=False), ns, a.reps), 10, unroll=unroll)
-        report("flow_sde_rollout_x0_noround", timeit(lambda i: flow(i, SRC_NOISE, flags=0), ns, a.reps), 16, unroll=unroll)
-    lib.mixgrpo_set_tuning(0, 2)
+    kw = {}
+    report("flow_sde_rollout_x0", timeit(lambda i: flow(i, SRC_NOISE), ns, a.reps), 16, **kw)
+    report("flow_sde_rollout_x0_graph", graph_time(lambda i: flow(i, SRC_NOISE)), 16, **kw)
+    report("flow_sde_rollout_nox0_graph", graph_time(lambda i: flow(i, SRC_NOISE, x0=False)), 12, **kw)
+    report("flow_ode_rollout_x0_graph", graph_time(lambda i: flow(i, SRC_DETERMINISTIC)), 14, **kw)
+    report("flow_ode_rollout_nox0_graph", graph_time(lambda i: flow(i, SRC_DETERMINISTIC, x0=False)), 10, **kw)
+    report("flow_train_fwd", timeit(lambda i: flow(i, SRC_GIVEN, x0=False), ns, a.reps), 10, **kw)
+    report("flow_train_fwd_graph", graph_time(lambda i: flow(i, SRC_GIVEN, x0=False)), 10, **kw)
+    report("flow_sde_rollout_x0_noround_graph", graph_time(lambda i: flow(i, SRC_NOISE, flags=0)), 16, **kw)
     report("logprob_bwd", timeit(bwd, ns, a.reps), 12)
-    if a.graph:
-        # same launches replayed from a CUDA graph (launch overhead removed): ns launches per replay
-        for unroll in (1, 2, 4):
-            lib.mixgrpo_set_tuning(0, unroll)
-            s = torch.cuda.Stream()
-            with torch.cuda.stream(s):
-                st_old = st
-                st = s.cuda_stream
-                flow(0, SRC_NOISE)
-                torch.cuda.synchronize()
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=s):
-                    st = torch.cuda.current_stream().cuda_stream
-                    for i in range(ns):
-                        flow(i, SRC_NOISE)
-                st = st_old
-                us = timeit(lambda i: gr.replay(), 1, max(a.reps // ns, 10), warm=3) / ns
-            report("flow_sde_rollout_x0_graph", us, 16, unroll=unroll)
-        lib.mixgrpo_set_tuning(0, 2)
+    report("logprob_bwd_graph", graph_time(bwd), 12)
 
 
 if __name__ == "__main__":
