@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py — MixGRPO rollout + policy-update hot path on B200 (driver contract: one JSON line).
+
+Workload (BASELINE.json configs[1]): FLUX.1-dev-shape 1024^2 packed latents (12, 4096, 64), group size 12,
+25 sampling steps, SDE window 4, bf16 model output and noise, fp32 latents.  One bench "step" = one GRPO
+iteration's hot path for the prompt group(s) this rank owns, on synthetic random-init tensors:
+
+  rollout        25 fused sampler steps (21 Euler-ODE + 4 SDE with log-prob), each reading a distinct
+                 pre-generated model output v_i and writing all_latents[:, i+1] in place
+  exchange       ONE all_gather_into_tensor of the [3 models x 12] rewards          (N > 1 only)
+  advantages     group-relative, 3 reward models, weighted                         (1 launch)
+  policy update  for each of the 4 window steps: log-prob forward, clipped-ratio loss fwd+bwd, log-prob
+                 backward -> grad wrt model output                                 (3 launches each)
+  logging        ONE [4] all_reduce(AVG) of loss/policy/kl/clip_frac               (N > 1 only)
+
+metric  = sampler-step latent GB/s = algorithmic bytes of all sampler/log-prob kernels in the step
+          (SURVEY.md §8d per-element figures) / step time, summed over ranks ("weak" scaling: each rank
+          owns its own prompt groups; no data-path collective).  rollout_steps_per_s is reported beside it.
+roofline= the fused SDE step + log-prob kernel with the reference's full output signature
+          (prev_sample, pred_x0, log_prob: 16 B/elem), timed by CUDA events over graph replays on
+          rotating buffer sets larger than L2.
+e2e     = the same step through the public Python API with HOST (pinned) model outputs/noise/rewards,
+          H2D + D2H copies inside the timed region.
+--impl reference: the reference's algorithm on the host cores (oracle/: torch-CPU restatement pinned
+          bit-exact to the reference — the reference itself is pure PyTorch, so this IS its CPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+B, S, C = 12, 4096, 64          # group size, packed tokens (1024^2), channels
+N_STEPS, WINDOW, N_MODELS = 25, 4, 3
+ETA, SHIFT = 0.7, 3.0
+CLIP, ADV_CLIP, KL, GA = 1e-4, 5.0, 0.01, 3
+BYTES = {"ode": 10, "sde": 12, "sde_x0": 16, "train_fwd": 10, "bwd": 12}   # SURVEY §8d, bf16 v/noise
+
+
+def algorithmic_bytes_per_step() -> int:
+    e = B * S * C
+    return e * ((N_STEPS - WINDOW) * BYTES["ode"] + WINDOW * BYTES["sde"] + WINDOW * (BYTES["train_fwd"] + BYTES["bwd"]))
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback"
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "step_kernel_ncu.json"
+    try:
+        d = json.loads(p.read_text())
+        return d["dram_bytes_read"] + d["dram_bytes_write"], d.get("note", "")
+    except Exception:  # noqa: BLE001
+        return None, "no ncu capture committed"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for nm, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ native arm
+class Workload:
+    """Device-resident synthetic tensors of the configs[1] shape (random-init; there is no dataset)."""
+
+    def __init__(self, dev, rank: int):
+        from mixgrpo_b200 import rollout as R
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.dev = dev
+        self.cfg = R.SamplerConfig(sampling_steps=N_STEPS, eta=ETA, shift=SHIFT)
+        self.sig = R.sigma_schedule(N_STEPS, SHIFT)                        # host schedule: no per-step sync
+        self.z0 = torch.randn(B, S, C, device=dev, generator=g).bfloat16()
+        self.v = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(N_STEPS)]   # 25 x 6.3 MB
+        self.eps = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(WINDOW)]
+        self.rewards = torch.randn(N_MODELS, B, device=dev, generator=g)
+        self.weights = torch.tensor([1.0, 0.5, 2.0], device=dev)
+        self.stats = torch.zeros(4, device=dev)
+
+    def noises(self, window):
+        nz = [None] * N_STEPS
+        for j, i in enumerate(window):
+            nz[i] = self.eps[j]
+        return nz
+
+
+def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=None, collectives=True):
+    """One GRPO iteration's hot path through the public API (mixgrpo_b200.rollout / .grpo)."""
+    from mixgrpo_b200 import grpo, rollout as R
+    v_list = v_list if v_list is not None else w.v
+    det = R.window_mask(N_STEPS, window)
+    nz = [None] * N_STEPS
+    for j, i in enumerate(window):
+        nz[i] = (eps if eps is not None else w.eps)[j]
+    _, _, traj, logps, _ = R.rollout(lambda lat, s, i: v_list[i], w.z0, w.sig, det, w.cfg, noises=nz)
+    rew = rewards if rewards is not None else w.rewards
+    if collectives and dist.is_initialized() and dist.get_world_size() > 1:
+        gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
+        _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
+    adv = grpo.compute_group_advantages(rew, B, w.weights)
+    w.stats.zero_()
+    grads = []
+    for t in window:
+        _, _, gv = R.policy_update(v_list[t], traj[:, t], traj[:, t + 1], logps[:, t], adv, w.sig, t, w.cfg, clip_range=CLIP,
+                                   adv_clip_max=ADV_CLIP, kl_coeff=KL, gradient_accumulation_steps=GA,
+                                   num_train_timesteps=len(window), stats_accum=w.stats)
+        grads.append(gv)
+    if collectives:
+        grpo.reduce_step_stats(w.stats, group)
+    return w.stats, logps, grads
+
+
+LAUNCHES_PER_STEP = N_STEPS + 1 + 3 * WINDOW     # our kernels: 25 sampler + 1 advantage + 4 x (fwd, loss, bwd)
+
+
+def capture_step(w: Workload, window):
+    """The device part of a step as a CUDA graph (collectives stay outside the graph)."""
+    s = torch.cuda.Stream(device=w.dev)
+    s.wait_stream(torch.cuda.current_stream(w.dev))
+    with torch.cuda.stream(s):
+        native_step(w, window, collectives=False)  # warm-up on the capture stream (allocations, workspaces, coef tables)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out = native_step(w, window, collectives=False)
+    torch.cuda.current_stream(w.dev).wait_stream(s)
+    return g, out
+
+
+def measure_roofline(dev, peak_gbs, peak_kind):
+    """CUDA-event time per launch of the fused SDE step + log-prob kernel (16 B/elem signature) and its siblings,
+    replayed from a CUDA graph over 10 rotating buffer sets (10 x 50 MB > 126 MB L2)."""
+    from mixgrpo_b200 import coefs, ops
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+    ns = 10
+    g = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.randn(B, S, C, device=dev, generator=g) for _ in range(ns)]
+    vs = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(ns)]
+    es = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(ns)]
+    outs = [torch.empty(B, S, C, device=dev) for _ in range(ns)]
+    lps = torch.empty(ns, B, device=dev)
+    glp = torch.randn(B, device=dev)
+    sig = torch.linspace(1, 0, N_STEPS + 1)
+    sig = (SHIFT * sig) / (1 + (SHIFT - 1) * sig)
+    k, _ = coefs.flow(sig, 9, ETA, "ref_cuda", True)
+    e = B * S * C
+
+    def run(kind, i):
+        if kind == "sde_x0":
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, round_like_torch=True)
+        elif kind == "sde":
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=False, round_like_torch=True)
+        elif kind == "ode":
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], out_logp=lps[i], want_x0=False, round_like_torch=True)
+        elif kind == "train_fwd":
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_GIVEN, x_next=outs[(i + 1) % ns], out_logp=lps[i], want_x0=False, round_like_torch=True)
+        elif kind == "bwd":
+            ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True)
+
+    res = {}
+    s = torch.cuda.Stream(device=dev)
+    for kind in ("sde_x0", "sde", "ode", "train_fwd", "bwd"):
+        with torch.cuda.stream(s):
+            for i in range(ns):
+                run(kind, i)
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for i in range(ns):
+                    run(kind, i)
+            for _ in range(3):
+                gr.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            a.record(s)
+            for _ in range(reps):
+                gr.replay()
+            b.record(s)
+            b.synchronize()
+            us = a.elapsed_time(b) * 1e3 / (reps * ns)
+        res[kind] = {"us_per_launch": round(us, 3), "bytes_per_elem": BYTES[kind], "GBps": round(e * BYTES[kind] / us / 1e3, 1)}
+        del gr
+    top = res["sde_x0"]
+    roof = {"bound": "hbm", "kernel": "mg::step_kernel<flow, bf16, SRC_NOISE> (fused SDE step + log-prob -> prev_sample, pred_x0, log_prob)",
+            "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+            "unit": "GB/s", "frac": round(top["GBps"] / peak_gbs, 4), "traffic": None, "us_per_launch": top["us_per_launch"],
+            "algorithmic_bytes_per_launch": e * 16, "how": "CUDA events around 20 replays of a 10-launch CUDA graph over rotating buffer sets (500 MB > L2)"}
+    return roof, res
+
+
+def e2e_run(w: Workload, window, steps: int, warmup: int):
+    """Same step with HOST inputs: every step copies its 25 model outputs, 4 noise tensors and the rewards from pinned
+    host memory, runs through the public API (eager launches), and reads stats + log-probs back."""
+    hv = [torch.empty(B, S, C, dtype=torch.bfloat16).pin_memory() for _ in range(N_STEPS)]
+    he = [torch.empty(B, S, C, dtype=torch.bfloat16).pin_memory() for _ in range(WINDOW)]
+    hr = torch.randn(N_MODELS, B).pin_memory()
+    for t in hv + he:
+        t.normal_()
+    dv = [torch.empty_like(t, device=w.dev) for t in hv]
+    de = [torch.empty_like(t, device=w.dev) for t in he]
+    dr = torch.empty(N_MODELS, B, device=w.dev)
+    h_stats = torch.empty(4).pin_memory()
+    h_lp = torch.empty(B, N_STEPS).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in hv + he) + hr.numel() * 4
+    d2h = h_stats.numel() * 4 + h_lp.numel() * 4
+    copy_stream = torch.cuda.Stream(device=w.dev)
+    main = torch.cuda.current_stream(w.dev)
+
+    def one():
+        # H2D on a copy stream, one event per tensor, so step i's kernel only waits for ITS model output
+        evs = []
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            dr.copy_(hr, non_blocking=True)
+            for j in range(WINDOW):
+                de[j].copy_(he[j], non_blocking=True)
+            for i in range(N_STEPS):
+                dv[i].copy_(hv[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                evs.append(ev)
+
+        class Lazy(list):
+            def __getitem__(self, i):
+                main.wait_event(evs[i])
+                return dv[i]
+        main.wait_event(evs[0])
+        stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=de, rewards=dr)
+        h_stats.copy_(stats, non_blocking=True)
+        h_lp.copy_(logps, non_blocking=True)
+        main.synchronize()
+        return float(h_stats[0])
+
+    for _ in range(warmup):
+        one()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = one()
+    torch.cuda.synchronize(w.dev)
+    dt = time.perf_counter() - t0
+    return dt / steps, h2d, d2h, loss
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(x: float, dev) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_native(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: a CUDA device is required (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mixgrpo_b200
+    from mixgrpo_b200 import ops
+    from mixgrpo_b200.grpo_states import GRPOTrainingStates
+    mixgrpo_b200.load_library()
+    peak, peak_kind = load_peaks()
+    w = Workload(dev, rank)
+    states = GRPOTrainingStates(iters_per_group=25, group_size=WINDOW, max_timesteps=N_STEPS - 2, prog_overlap=True, prog_overlap_step=1)
+    window = states.get_current_timesteps()
+
+    graph, (stats, logps, _) = capture_step(w, window)
+
+    def step():
+        graph.replay()
+        if world > 1:                                                   # the path's two tiny collectives, outside the graph
+            from mixgrpo_b200 import grpo
+            grpo.gather_rewards(w.rewards)
+            grpo.reduce_step_stats(w.stats)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    barrier()
+    torch.cuda.synchronize(dev)
+    with ClockSampler(local) as clk:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # keep the region long enough for nvidia-smi to sample it: repeat the K steps inside the region is NOT allowed,
+        # so K is what it is; clocks are additionally sampled over the roofline loop below
+        torch.cuda.profiler.start()              # `ncu --profile-from-start off` captures exactly the timed region
+        a.record()
+        for _ in range(args.steps):
+            step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        barrier()
+        ms = a.elapsed_time(b)
+        if args.profile_only:
+            if rank == 0:
+                print(json.dumps({"profile_only": True, "steps": args.steps, "ms_per_step": ms / args.steps}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            return
+        roof, kernels = measure_roofline(dev, peak, peak_kind) if rank == 0 else (None, None)
+        if roof is not None:
+            roof["traffic"], roof["traffic_note"] = load_ncu_traffic()
+    ms_per_step = max_over_ranks(ms / args.steps, dev)
+    total_bytes = algorithmic_bytes_per_step() * world
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    loss_host = float(stats[0].item())
+
+    e2e_s, h2d, d2h, e2e_loss = e2e_run(w, window, max(2, min(args.steps, 5)), 2)
+    e2e_s = max_over_ranks(e2e_s, dev)
+    e2e_value = total_bytes / e2e_s / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_step(1, 1)
+    if rank == 0:
+        line = {
+            "metric": "sampler-step latent GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
+            "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
+                                   "one prompt group per GPU", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
+                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group",
+                       "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
+            "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
+            "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
+            "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages + rollout.policy_update (eager)"},
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "clocks": clk.summary(), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "check": {"loss": loss_host, "e2e_loss": e2e_loss, "logp_mean": float(logps[:, window[0]].mean().item())},
+            "library": mixgrpo_b200.library_path(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_step(steps: int, warmup: int):
+    """The reference's algorithm for the same step on the host cores (oracle = torch-CPU restatement pinned
+    bit-exact to the reference's own functions).  Returns the cpu_baseline object."""
+    from oracle import grpo_oracle as GO
+    from oracle import sampling_oracle as O
+    g = torch.Generator().manual_seed(1234)
+    sig = O.sd3_time_shift(SHIFT, torch.linspace(1, 0, N_STEPS + 1))
+    z0 = torch.randn(B, S, C, generator=g).bfloat16()
+    v = [torch.randn(B, S, C, generator=g).bfloat16() for _ in range(N_STEPS)]
+    window = list(range(WINDOW))
+    eps = {i: torch.randn(B, S, C, generator=g).bfloat16() for i in window}
+    rewards = {f"m{j}": torch.randn(B, generator=g) for j in range(N_MODELS)}
+    weights = {"m0": 1.0, "m1": 0.5, "m2": 2.0}
+    det = [i not in window for i in range(N_STEPS)]
+
+    def one():
+        with torch.no_grad():
+            _, _, traj, logps = O.rollout(lambda z, s, i: v[i], z0, sig, det, [eps.get(i, z0) for i in range(N_STEPS)], eta=ETA, shift=SHIFT)
+        adv = GO.group_advantages(rewards, B, weights)
+        tot = 0.0
+        for t in window:
+            vt = v[t].clone().requires_grad_(True)
+            lp = O.flow_step(vt, traj[:, t], ETA, sig, t, traj[:, t + 1])[2]
+            loss = sum(GO.grpo_loss(lp[i:i + 1], logps[i:i + 1, t], adv[i:i + 1], CLIP, ADV_CLIP, KL, GA, len(window))[0] for i in range(B))
+            loss.backward()
+            tot += float(loss.detach())
+        return tot
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = one()
+    dt = (time.perf_counter() - t0) / steps
+    gbs = algorithmic_bytes_per_step() / dt / 1e9
+    return {"value": round(gbs, 4), "unit": "GB/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{steps} full step(s) of the same workload (25 sampler steps at (12,4096,64) + advantages + 4 window updates with autograd), "
+                      f"{warmup} warm-up", "s_per_step": round(dt, 3), "loss": loss,
+            "note": "oracle/ = torch-CPU restatement, bit-exact vs the reference's own functions (tests/test_oracle_pin.py); the reference is pure PyTorch"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    cpu = cpu_reference_step(args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "sampler-step latent GB/s", "value": cpu["value"], "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cpu["s_per_step"] * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
+            "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1])",
+                       "device": "host CPU cores (reference PyTorch path)"},
+            "rollout_steps_per_s": round(B * N_STEPS / cpu["s_per_step"], 2), "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="setup + warm-up + K timed steps between cudaProfilerStart/Stop, then exit (for ncu)")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 200
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

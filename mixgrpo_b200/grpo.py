@@ -41,12 +41,25 @@ def gather_rewards(rewards: RewardsLike, group: Optional[dist.ProcessGroup] = No
     else:
         world = dist.get_world_size(group)
         mat = mat.contiguous()
-        buf = torch.empty((world,) + tuple(mat.shape), dtype=mat.dtype, device=mat.device)
+        buf = torch.empty((world * mat.shape[0], mat.shape[1]), dtype=mat.dtype, device=mat.device)   # rank-major rows
         dist.all_gather_into_tensor(buf, mat, group=group)
-        gathered = buf.permute(1, 0, 2).reshape(mat.shape[0], -1)      # [n_models, world*local_B]
+        gathered = buf.view(world, mat.shape[0], mat.shape[1]).permute(1, 0, 2).reshape(mat.shape[0], -1)   # [n_models, world*local_B]
     if names is None:
         return gathered.reshape(-1) if (isinstance(rewards, torch.Tensor) and rewards.dim() == 1) else gathered
     return {k: gathered[i] for i, k in enumerate(names)}
+
+
+_weight_cache: Dict[Tuple, torch.Tensor] = {}
+
+
+def _weights_on(device: torch.device, w: Tuple[float, ...]) -> torch.Tensor:
+    """Reward weights as a cached device vector (one H2D copy per distinct weight tuple, not per step)."""
+    key = (device.type, device.index, w)
+    t = _weight_cache.get(key)
+    if t is None:
+        t = torch.tensor(w, dtype=torch.float32).to(device)
+        _weight_cache[key] = t
+    return t
 
 
 def compute_group_advantages(rewards: RewardsLike, num_generations: int,
@@ -68,11 +81,13 @@ def compute_group_advantages(rewards: RewardsLike, num_generations: int,
         stat = gathered_rewards if gathered_rewards is not None else mat.reshape(-1)
         return _ops.group_advantages(mat, None, 1, 0, use_group=False, stat_rewards=stat)
     weights = None
-    if names is not None:
+    if torch.is_tensor(reward_weights):                                     # already a device vector [n_models]
+        weights = reward_weights
+    elif names is not None or (reward_weights is not None and mat.shape[0] > 1):
         if reward_weights is None:
             raise ValueError("reward_weights is required for multi-reward (advantage_aggr) rewards")
-        w = [float(reward_weights[k]) for k in names] if isinstance(reward_weights, dict) else [float(x) for x in reward_weights]
-        weights = torch.tensor(w, dtype=torch.float32).to(mat.device, non_blocking=True)
+        w = tuple(float(reward_weights[k]) for k in names) if isinstance(reward_weights, dict) else tuple(float(x) for x in reward_weights)
+        weights = _weights_on(mat.device, w)
     trim = 0
     if trimmed_ratio > 0:                                                   # TR:451-454
         trim = min(int(num_generations * trimmed_ratio), num_generations - 1)

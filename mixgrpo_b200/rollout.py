@@ -176,7 +176,7 @@ def balance_pos_neg(samples: List[dict], use_random: bool = False, rng: Optional
 def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Tensor, old_log_probs: torch.Tensor,
                   advantages: torch.Tensor, sigmas: torch.Tensor, index: int, cfg: SamplerConfig, *, clip_range: float,
                   adv_clip_max: float, kl_coeff: float, gradient_accumulation_steps: int, num_train_timesteps: int,
-                  stats_accum: Optional[torch.Tensor] = None):
+                  stats_accum: Optional[torch.Tensor] = None, per_sample_loss: bool = True):
     """One (samples, window step) policy update, TR:542-585 without autograd: given the model output ``v`` for
     the stored ``latents`` it returns ``(stats[4], new_log_probs [B], grad_v)`` where ``grad_v`` is
     dloss/dv — hand it to ``v.backward(grad_v)`` to continue into the DiT.  Three kernel launches, no sync."""
@@ -190,7 +190,13 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     vd = v.detach()
     _, _, new_lp, _ = _ops.fused_step(fam, vd, latents, k, src=SRC_GIVEN, x_next=next_latents, want_x0=False,
                                       sde_solver=True, round_like_torch=rnd)
-    stats, g_lp = _grpo.grpo_loss_and_grad(new_lp, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
-                                           gradient_accumulation_steps, num_train_timesteps, stats_accum=stats_accum)
+    # The reference evaluates the loss one sample at a time (B == 1 per call, TR:536-585) and lets autograd
+    # accumulate: sum_i loss_i / (GA*T).  A batch of B samples in one launch is the same thing with the mean's
+    # 1/B folded into the denominator; stats[0..2] are then the SUMS over the batch (what TR:588-596 add up).
+    denom = float(gradient_accumulation_steps * num_train_timesteps)
+    if per_sample_loss:
+        denom /= v.shape[0]
+    stats, g_lp = _ops.grpo_loss_fwd_bwd(new_lp, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff, denom,
+                                         want_grad=True, stats_accum=stats_accum)
     grad_v = _ops.logprob_backward(fam, vd, latents, next_latents, g_lp, k, rnd)
     return stats, new_lp, grad_v

@@ -1,0 +1,89 @@
+"""C-ABI library: loads on a CPU-only box, exports every symbol include/mixgrpo_b200.h declares, and
+rejects bad arguments before touching CUDA (no compute calls without a GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "mixgrpo_b200.h").read_text()
+
+
+def _declared():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(mixgrpo_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_header_and_binding_agree():
+    from mixgrpo_b200 import _cabi
+    assert _declared() == sorted(_cabi.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_library_builds_loads_and_exports_all_symbols():
+    from mixgrpo_b200 import _build, _cabi
+    lib_path = _build.build()
+    h = ctypes.CDLL(str(lib_path))
+    for name in _declared():
+        assert hasattr(h, name), f"{name} not exported"
+    lib = _cabi.lib()
+    assert lib.mixgrpo_abi_version() == _cabi.ABI_VERSION
+    assert b"sm_100a" in lib.mixgrpo_build_info()
+    assert lib.mixgrpo_error_string(0) == b"success"
+    assert b"invalid" in lib.mixgrpo_error_string(-1)
+
+
+def test_sass_is_sm100a_with_256bit_accesses():
+    """The shipped cubin targets sm_100a and the step kernel uses LDG.E.256 / STG.E.256 (Blackwell-only widths)."""
+    import shutil
+    import subprocess
+    from mixgrpo_b200 import _build
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = str(_build.build())
+    elf = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2mg11step_kernelILi0E13__nv_bfloat16S1_Li0ELi1ELb1ELb0ELb1ELb0EEEvNS_10StepParamsE", lib],
+                          capture_output=True, text=True).stdout
+    assert ".256" in sass and "LDG" in sass and "STG" in sass
+
+
+def test_host_side_argument_validation_needs_no_gpu():
+    from mixgrpo_b200 import _cabi
+    lib = _cabi.lib()
+    k = _cabi.StepCoefs()
+    assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 256
+    assert lib.mixgrpo_step_workspace_bytes(0, 10) == 0
+    assert lib.mixgrpo_step_workspace_bytes(100, 10) == 1024
+    # null pointers / bad sizes / bad enums are rejected with MIXGRPO_EINVAL before any launch
+    assert lib.mixgrpo_flow_step(None, 1, None, 0, None, None, 0, None, 0, None, None, None, None, 0, 1, 8, ctypes.byref(k), 0, 0, None) == -1
+    assert lib.mixgrpo_dpm_step(1, 1, 1, 8, None, None, None, 4, None, 8, None, None, None, None, 0, 1, 8, ctypes.byref(k), 2, 0, None) == -1
+    assert lib.mixgrpo_logprob_bwd(7, 1, 1, 1, 8, 1, 8, 1, 1, 1, 8, ctypes.byref(k), 0, None) == -1
+    assert lib.mixgrpo_group_advantages(None, None, 1, 4, 4, 0, 1, None, 0, None, None) == -1
+    assert lib.mixgrpo_grpo_loss(None, None, None, 1, 1e-4, 5.0, 0.0, 12.0, None, None, None, None) == -1
+    assert lib.mixgrpo_pack_latents(None, None, 0, 1, 16, 8, 8, None) == -1
+    assert lib.mixgrpo_set_tuning(99, 1) == -1
+
+
+def test_python_layer_refuses_cpu_tensors():
+    import torch
+    from mixgrpo_b200 import grpo, ops, sampling_utils as su
+    x = torch.zeros(1, 4, 64)
+    sig = torch.linspace(1, 0, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        su.flow_grpo_step(x.bfloat16(), x, 0.7, sig, 1, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        su.dance_grpo_step(x.bfloat16(), x, 0.7, sig, 1, x, True, True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        grpo.compute_group_advantages(torch.zeros(4), 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        grpo.grpo_loss(torch.zeros(2), torch.zeros(2), torch.zeros(2), 1e-4, 5.0, 0.0, 1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pack_latents(torch.zeros(1, 16, 4, 4), 1, 16, 4, 4)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not route through the oracle (or any CPU fallback)."""
+    for f in (ROOT / "mixgrpo_b200").rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f

@@ -223,7 +223,12 @@ def test_full_size_properties_1024sq_group12():
     # Euler ODE: prev(v) - x is odd in v
     o1 = su.flow_grpo_step(v, x, ETA, SIG, idx, None, determistic=True)[0]
     o2 = su.flow_grpo_step(-v, x, ETA, SIG, idx, None, determistic=True)[0]
-    assert torch.equal(o1 - x, -(o2 - x))
+    # x' = x + bf16(dt*v): the increments are exactly opposite; after the fp32 add they differ by rounding only
+    assert ((o1 - x) + (o2 - x)).abs().max() <= 2 * torch.finfo(torch.float32).eps * (x.abs().max() + 1)
+    # and the deterministic step is reproducible bit-for-bit across launches (packed-atomic log-prob included)
+    r1 = su.flow_grpo_step(v, x, ETA, SIG, idx, None, noise=eps)
+    r2 = su.flow_grpo_step(v, x, ETA, SIG, idx, None, noise=eps)
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[2], r2[2])
 
 
 def test_advantages_vs_oracle():

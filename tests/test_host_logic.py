@@ -1,0 +1,154 @@
+"""Host-side logic of the product package (no GPU): per-step coefficient tables vs the oracle's zero-dim
+scalars, schedule construction, window masks, sample bookkeeping, reward stacking."""
+import random
+import types
+
+import pytest
+import torch
+
+from mixgrpo_b200 import coefs, grpo, rollout as R
+from mixgrpo_b200 import sampling_utils as su
+from oracle import grpo_oracle as GO
+from oracle import sampling_oracle as O
+
+SIG = O.sd3_time_shift(3.0, torch.linspace(1, 0, 26))
+
+
+def _bf(x):
+    return torch.tensor(x).bfloat16().float().item()
+
+
+@pytest.mark.parametrize("index", [0, 1, 5, 12, 23, 24])
+def test_flow_coefficients_match_oracle_scalars(index):
+    x = torch.zeros(1, 2, 64)
+    _, _, _, _, scale = O.flow_step(x, x, 0.7, SIG, index, x)
+    k, sc = coefs.flow(SIG, index, 0.7, "fp32", False)
+    assert sc == scale.item()
+    s, sn = SIG[index], SIG[index + 1]
+    dt = sn - s
+    std = torch.sqrt(s / (1 - torch.where(s == 1, SIG[1].item(), s))) * 0.7
+    assert k.c[0] == s.item() and k.c[3] == dt.item() and k.c[5] == dt.item()
+    assert k.c[1] == (1 + std ** 2 / (2 * s) * dt).item()
+    assert k.c[2] == (1 + std ** 2 * (1 - s) / (2 * s)).item()
+    assert k.two_var == (2 * (scale ** 2)).item()
+    assert k.log_scale == torch.log(scale).item()
+    # rounding modes only touch the factors torch would cast to bf16
+    kc, _ = coefs.flow(SIG, index, 0.7, "ref_cpu", True)
+    kg, _ = coefs.flow(SIG, index, 0.7, "ref_cuda", True)
+    assert (kc.c[0], kc.c[4], kc.c[5]) == (_bf(k.c[0]), _bf(k.c[4]), _bf(k.c[5]))
+    assert (kc.c[1], kc.c[2], kc.c[3]) == (k.c[1], k.c[2], k.c[3])
+    assert (kg.c[2], kg.c[3]) == (_bf(k.c[2]), _bf(k.c[3])) and kg.c[1] == k.c[1]
+    kf, _ = coefs.flow(SIG, index, 0.7, "ref_cuda", False)          # fp32 model output: nothing is rounded
+    assert list(kf.c) == list(k.c)
+
+
+def test_schedule_cache_is_value_safe():
+    a = O.sd3_time_shift(3.0, torch.linspace(1, 0, 26))
+    k1, _ = coefs.flow(a, 3, 0.7, "fp32", False)
+    a[4] = 0.5                                    # in-place edit bumps _version -> new host copy, new coefficients
+    k2, _ = coefs.flow(a, 3, 0.7, "fp32", False)
+    assert k1.c[3] != k2.c[3]
+    b = O.sd3_time_shift(2.0, torch.linspace(1, 0, 26))
+    k3, _ = coefs.flow(b, 3, 0.7, "fp32", False)
+    assert k3.c[0] == b[3].item()
+
+
+def test_dpm_coefficients_reproduce_oracle_update_on_cpu():
+    """Evaluate the folded-sign coefficient form with plain torch and compare with the oracle's formulas."""
+    g = torch.Generator().manual_seed(0)
+    for algo in ("dpmsolver++", "dpmsolver"):
+        for stype in ("midpoint", "heun"):
+            for order in (1, 2, 3):
+                if algo == "dpmsolver" and order == 3:
+                    with pytest.raises(UnboundLocalError):
+                        coefs.dpm(SIG, 5, 3, algo, stype, "fp32", False)
+                    continue
+                i = 7
+                x = torch.randn(2, 4, 64, generator=g)
+                m = [torch.randn(2, 4, 64, generator=g) for _ in range(3)]          # m[-1] = m0 (current x0)
+                nz = torch.randn(2, 4, 64, generator=g)
+                k, sc = coefs.dpm(SIG, i, order, algo, stype, "fp32", False)
+                c = [torch.tensor(v) for v in k.c]
+                m0, m1, m2 = m[2], m[1], m[0]
+                d1 = d2 = torch.zeros_like(x)
+                if order == 2:
+                    d1 = c[1] * (m0 - m1)
+                if order == 3:
+                    d10, d11 = c[1] * (m0 - m1), c[2] * (m1 - m2)
+                    d1, d2 = d10 + c[3] * (d10 - d11), c[4] * (d10 - d11)
+                mean = c[5] * x + c[6] * m0
+                ode = c[9] * x + c[10] * m0
+                if order >= 2:
+                    mean, ode = mean + c[7] * d1, ode + c[11] * d1
+                if order == 3:
+                    mean, ode = mean + c[8] * d2, ode + c[12] * d2
+                for sde in (False, True):
+                    if order == 1:
+                        ref = O.dpm_first_order(algo, m0, SIG, i, x, nz, sde)
+                    elif order == 2:
+                        ref = O.dpm_second_order(algo, stype, m, SIG, i, x, nz, sde)
+                    else:
+                        ref = O.dpm_third_order(algo, m, SIG, i, x, nz, sde)
+                    got = mean + c[13] * nz if sde else ode
+                    assert torch.equal(got, ref[0]), (algo, stype, order, sde)
+                    assert torch.equal(mean, ref[1])
+                    assert sc == (ref[2] * ref[3]).item()
+
+
+def test_flash_schedule_and_order_selection():
+    args = types.SimpleNamespace(dpm_post_compress_ratio=0.4, shift=3.0, dpm_solver_order=2)
+    det = [True] * 25
+    for i in (2, 3, 4, 5):
+        det[i] = False
+    mine, last = su._flash_schedule(args, SIG, det)
+    ref, rlast = O.flash_schedule(SIG, det, 3.0, 0.4)
+    assert last == rlast == 5 and torch.equal(mine, ref) and mine.numel() == 6 + 8
+    st = su.DPMState(order=2)
+    assert su._dpm_order(args, 0, 12, st) == 1
+    st.lower_order_nums = 1
+    assert su._dpm_order(args, 6, 12, st) == 2 and su._dpm_order(args, 11, 12, st) == 1
+    assert su._dpm_order(args, 6, 12, None) == 1
+    args.dpm_solver_order = 3
+    st = su.DPMState(order=3)
+    st.lower_order_nums = 2
+    assert su._dpm_order(args, 5, 25, st) == 3 and su._dpm_order(args, 10, 12, st) == 2
+
+
+def test_window_mask_and_schedule():
+    assert R.window_mask(6, [1, 2]) == [True, False, False, True, True, True]
+    assert R.window_mask(3, [], "all") == [False] * 3
+    assert torch.equal(R.sigma_schedule(25, 3.0), SIG)
+
+
+def test_balance_pos_neg_matches_reference():
+    from oracle import ref_loader
+    ru = ref_loader.load_reward_utils()
+    samples = [{"advantages": torch.tensor([a]), "id": i} for i, a in enumerate([0.3, -1.2, 0.0, 2.0, -0.1, -0.7, 0.9, -3.0, -0.2])]
+    mine = R.balance_pos_neg(samples, rng=random.Random(5))
+    ids = [s["id"] for s in mine]
+    assert sorted(ids) == [0, 1, 3, 4, 5, 6, 7, 8]                      # the zero-advantage sample is dropped
+    signs = [samples[i]["advantages"].item() > 0 for i in ids]
+    assert signs[:6] == [True, False] * 3 and not any(signs[6:])         # interleaved, then the larger group's rest
+    if ru is not None:
+        for use_random in (False, True):
+            random.seed(123)
+            ref = ru.balance_pos_neg(list(samples), use_random=use_random)
+            random.seed(123)
+            got = R.balance_pos_neg(list(samples), use_random=use_random)
+            assert [s["id"] for s in ref] == [s["id"] for s in got]
+
+
+def test_make_samples_slices_and_reward_stacking():
+    lat = torch.arange(2 * 6 * 3, dtype=torch.float32).view(2, 6, 3)
+    lp = torch.arange(10, dtype=torch.float32).view(2, 5)
+    sig = O.sd3_time_shift(3.0, torch.linspace(1, 0, 6))
+    s = R.make_samples(lat, lp, sig, 5)
+    a, b, c = GO.sample_slices(lat, lp)
+    assert torch.equal(s["latents"], a) and torch.equal(s["next_latents"], b) and torch.equal(s["log_probs"], c)
+    assert s["timesteps"].tolist() == [[int(x * 1000) for x in sig][:5][:-1]] * 2
+    mat, names = grpo.stack_rewards({"a": torch.ones(4), "b": torch.zeros(4)})
+    assert names == ["a", "b"] and mat.shape == (2, 4)
+    single = grpo.gather_rewards(torch.arange(4.0))
+    assert torch.equal(single, torch.arange(4.0))                        # no process group: identity (TR:333-334)
+    d = grpo.gather_rewards({"a": torch.ones(3)})
+    assert list(d) == ["a"] and torch.equal(d["a"], torch.ones(3))

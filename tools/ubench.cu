@@ -288,6 +288,144 @@ template <int HINT> __global__ void __launch_bounds__(256) k_copy(const float* a
   if (i < n) { float r[8], s[8]; ld32<HINT>(a + i, r); ld32<HINT>(b2 + i, s); st32<HINT>(c + i, r); st32<HINT>(d + i, s); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Prototype: persistent CTA per SM, inputs staged by 1-D bulk async copies (cp.async.bulk -> UBLKCP) into a deep
+// shared-memory ring guarded by mbarriers, so (nearly) all of an SM's share of the input is in flight from t=0.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int STAGES, int CT /*consumer threads*/, int MATH>
+__global__ void __launch_bounds__(CT + 32, 1) k_sde_tma(const __grid_constant__ P p, int tiles_per_sample, int total_tiles) {
+  constexpr int TILE = 2048;
+  constexpr int EPT = TILE / CT;                 // elements per consumer thread per tile (4 for 512 threads)
+  static_assert(EPT == 4 || EPT == 8, "");
+  constexpr int STAGE_BYTES = TILE * 2 + TILE * 4 + TILE * 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + STAGES;
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(empty + STAGES);
+  unsigned* s_arr = reinterpret_cast<unsigned*>(s_acc + STAGES + 1);
+  unsigned char* ring = smem + 1024;
+  const int tid = threadIdx.x;
+  const long long n = p.n;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CT / 32); }
+    for (int s = 0; s <= STAGES; ++s) { s_acc[s] = 0ull; s_arr[s] = 0u; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // contiguous balanced share of the tiles
+  const int G = gridDim.x, c = blockIdx.x;
+  const int q = total_tiles / G, r = total_tiles % G;
+  const int t0 = c * q + min(c, r), t1 = t0 + q + (c < r ? 1 : 0);
+
+  if (tid >= CT) {                               // ---------------- producer warp
+    if (tid == CT) {
+      for (int t = t0, i = 0; t < t1; ++t, ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+        const int b = t / tiles_per_sample;
+        const long long off = (long long)(t - b * tiles_per_sample) * TILE;
+        const long long rem = n - off;
+        const uint32_t cnt = (uint32_t)(rem < TILE ? rem : TILE);
+        unsigned char* st = ring + (size_t)s * STAGE_BYTES;
+        mbar_expect_tx(&full[s], cnt * 8);
+        bulk_g2s(st, p.v + (long long)b * n + off, cnt * 2, &full[s]);
+        bulk_g2s(st + TILE * 2, p.x + (long long)b * n + off, cnt * 4, &full[s]);
+        bulk_g2s(st + TILE * 6, p.e + (long long)b * n + off, cnt * 2, &full[s]);
+      }
+    }
+    return;
+  }
+  // ---------------- consumers
+  const int lane = tid & 31;
+  float run_acc = 0.f;
+  int run_len = 0, run_id = 0;
+  for (int t = t0, i = 0; t < t1; ++t, ++i) {
+    const int s = i % STAGES;
+    const int b = t / tiles_per_sample;
+    const long long off = (long long)(t - b * tiles_per_sample) * TILE;
+    mbar_wait(&full[s], (i / STAGES) & 1);
+    const unsigned char* st = ring + (size_t)s * STAGE_BYTES;
+    float acc = 0.f;
+    const bool valid = off + (long long)tid * EPT < n;
+    if constexpr (EPT == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(st + tid * 8);
+      const float4 x = *reinterpret_cast<const float4*>(st + TILE * 2 + tid * 16);
+      const uint2 e = *reinterpret_cast<const uint2*>(st + TILE * 6 + tid * 8);
+      float xn[4], p0[4];
+      if constexpr (MATH == 1) {
+        acc += pair_math_b(p.c, p.cb, v.x, x.x, x.y, e.x, xn[0], xn[1], p0[0], p0[1]);
+        acc += pair_math_b(p.c, p.cb, v.y, x.z, x.w, e.y, xn[2], xn[3], p0[2], p0[3]);
+      } else {
+        acc += pair_math(p.c, lo(v.x), hi(v.x), x.x, x.y, lo(e.x), hi(e.x), xn[0], xn[1], p0[0], p0[1]);
+        acc += pair_math(p.c, lo(v.y), hi(v.y), x.z, x.w, lo(e.y), hi(e.y), xn[2], xn[3], p0[2], p0[3]);
+      }
+      if (valid) {
+        st16<H_NC_NA>(p.xo + (long long)b * n + off + tid * 4, xn[0], xn[1], xn[2], xn[3]);
+        st16<H_NC_NA>(p.x0 + (long long)b * n + off + tid * 4, p0[0], p0[1], p0[2], p0[3]);
+      }
+    } else {
+      const uint4 v = *reinterpret_cast<const uint4*>(st + tid * 16);
+      const float4 xa = *reinterpret_cast<const float4*>(st + TILE * 2 + tid * 32);
+      const float4 xb = *reinterpret_cast<const float4*>(st + TILE * 2 + tid * 32 + 16);
+      const uint4 e = *reinterpret_cast<const uint4*>(st + TILE * 6 + tid * 16);
+      float xn[8], p0[8];
+      acc += pair_math(p.c, lo(v.x), hi(v.x), xa.x, xa.y, lo(e.x), hi(e.x), xn[0], xn[1], p0[0], p0[1]);
+      acc += pair_math(p.c, lo(v.y), hi(v.y), xa.z, xa.w, lo(e.y), hi(e.y), xn[2], xn[3], p0[2], p0[3]);
+      acc += pair_math(p.c, lo(v.z), hi(v.z), xb.x, xb.y, lo(e.z), hi(e.z), xn[4], xn[5], p0[4], p0[5]);
+      acc += pair_math(p.c, lo(v.w), hi(v.w), xb.z, xb.w, lo(e.w), hi(e.w), xn[6], xn[7], p0[6], p0[7]);
+      if (valid) { st32<H_NC_NA>(p.xo + (long long)b * n + off + tid * 8, xn); st32<H_NC_NA>(p.x0 + (long long)b * n + off + tid * 8, p0); }
+    }
+    if (valid) run_acc += acc;
+    run_len += 1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);                         // stage can be refilled
+    const bool run_ends = (t + 1 == t1) || ((t + 1) / tiles_per_sample != b);
+    if (run_ends) {
+      // deterministic CTA reduction for this run of tiles without a barrier: every warp adds its fixed-point
+      // share to a shared-memory slot; the last warp to arrive publishes the run with ONE global atomic.
+      const float ws = warp_sum(run_acc);
+      if (lane == 0) {
+        const int slot = run_id % (STAGES + 1);
+        float rr = ws / ((float)n * p.c.two_var);
+        unsigned long long fx = (rr >= 0.f && rr <= 255.f) ? __float2ull_rn(rr * 4294967296.0f) : (1ull << 62);
+        atomicAdd(&s_acc[slot], fx);
+        __threadfence_block();
+        const unsigned old = atomicAdd(&s_arr[slot], 1u);
+        if (old == CT / 32 - 1) {
+          __threadfence_block();
+          unsigned long long tot = atomicExch(&s_acc[slot], 0ull);
+          s_arr[slot] = 0u;
+          unsigned long long add = (unsigned long long)run_len;
+          const unsigned long long capfx = (unsigned long long)(255.0 * 4294967296.0 * run_len / tiles_per_sample);
+          if (tot > capfx) { add += 1ull << 12; tot = 0; }
+          add += tot << 24;
+          const unsigned long long o = atomicAdd(&p.packed[b], add);
+          if ((o & 0xfffull) + run_len == (unsigned long long)tiles_per_sample) {
+            const unsigned long long tt = o + add;
+            float qv = (float)((double)(tt >> 24) * (1.0 / 4294967296.0));
+            if ((tt >> 12) & 0xfffull) qv = __int_as_float(0x7fc00000);
+            p.logp[b] = -qv - p.c.log_s - p.c.log_c;
+            p.packed[b] = 0ull;
+          }
+        }
+      }
+      run_acc = 0.f; run_len = 0; run_id += 1;
+    }
+  }
+}
+
 struct Bufs { __nv_bfloat16 *v, *e; float *x, *xo, *x0; };
 
 template <class F> static float time_graph(F launch, int nsets, int reps) {
@@ -316,6 +454,28 @@ static std::vector<Bufs> bufs;
 static float *d_logp, *d_partials; static unsigned* d_counters; static unsigned long long* d_packed;
 static Coef coef = {0.8125f, 0.9937f, 1.0234f, -0.0262f, 0.1367f, 0.0372f, -1.99f, 0.9189f};
 static CoefB coefb = {0x3f503f50u, 0x3f833f83u, 0xbcd7bcd7u, 0x3e0c3e0cu};
+
+template <int STAGES, int CT, int MATH>
+static void run_tma(const char* name, int grid_cap) {
+  constexpr int STAGE_BYTES = 2048 * 8;
+  const int tps = (int)((n + 2047) / 2048);
+  const int total = tps * B;
+  const size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES;
+  auto kern = k_sde_tma<STAGES, CT, MATH>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+  int grid = total < grid_cap ? total : grid_cap;
+  auto launch = [&](int i, cudaStream_t st) {
+    P p{bufs[i].v, bufs[i].x, bufs[i].e, bufs[i].xo, bufs[i].x0, d_logp, d_partials, d_counters, d_packed, n, tps, coef, coefb};
+    kern<<<grid, CT + 32, smem, st>>>(p, tps, total);
+  };
+  const float us = time_graph(launch, NS, REPS);
+  CK(cudaDeviceSynchronize());
+  const double gbs = (double)B * n * 16 / us / 1e3;
+  printf("%-34s STAGES=%d CT=%d MATH=%d grid=%d regs=%3d smem=%zuK  %7.2f us  %7.1f GB/s  %.3f\n", name, STAGES, CT, MATH, grid, fa.numRegs, smem / 1024, us, gbs, gbs / 6533.5);
+  fflush(stdout);
+}
+
 
 template <int VEC, int UNROLL, int HINT, int REDUCE, int BLOCK, int MINB, int MATH = 0>
 static void run(const char* name) {
@@ -364,26 +524,16 @@ int main(int argc, char** argv) {
     us = time_graph(launch2, NS, REPS);
     printf("%-34s %7.2f us  %7.1f GB/s  %.3f\n", "copy2x default hints", us, E * 16 / us / 1e3, E * 16 / us / 1e3 / 6533.5);
   }
-  //      VEC UNR HINT RED BLK MINB MATH
   run<8, 1, H_NC_NA, 0, 256, 6>("v8 u1 noreduce");
-  run<8, 1, H_NC_NA, 1, 256, 6>("v8 u1 ticket(CTA waits)");
-  run<8, 1, H_NC_NA, 4, 256, 6>("v8 u1 ticket warp0 lingers");
-  run<8, 1, H_NC_NA, 7, 256, 6>("v8 u1 packed atomic");
-  run<8, 1, H_NC_NA, 7, 256, 6, 1>("v8 u1 packed atomic hmul2");
-  run<8, 1, H_NC_NA, 7, 128, 12>("v8 u1 packed atomic b128");
-  run<8, 1, H_NC_NA, 7, 512, 3>("v8 u1 packed atomic b512");
-  run<8, 2, H_NC_NA, 7, 256, 4>("v8 u2 packed atomic");
-  run<4, 2, H_NC_NA, 7, 256, 8>("v4 u2 packed atomic minb8");
-  run<8, 1, H_NC_NA, 5, 288, 5>("v8 u1 ticket dedicated warp 288");
-  run<8, 1, H_NC_NA, 6, 256, 6>("v8 u1 partial store only");
-  run<8, 1, H_NC_NA, 0, 256, 6, 1>("v8 u1 noreduce hmul2");
-  run<8, 1, H_NC_NA, 4, 256, 6, 1>("v8 u1 warp0 lingers hmul2");
-  run<8, 1, H_NC_NA, 6, 256, 6, 1>("v8 u1 partial only hmul2");
-  run<8, 1, H_NC_NA, 4, 128, 12, 1>("v8 u1 warp0 lingers hmul2 b128");
-  run<8, 1, H_NC_NA, 4, 512, 3, 1>("v8 u1 warp0 lingers hmul2 b512");
-  run<8, 2, H_NC_NA, 4, 256, 4, 1>("v8 u2 warp0 lingers hmul2");
-  run<8, 2, H_NC_NA, 0, 256, 4, 1>("v8 u2 noreduce hmul2");
-  run<8, 1, H_NC_NA, 4, 256, 8, 1>("v8 u1 warp0 lingers hmul2 minb8");
-  run<8, 1, H_EVICT_FIRST, 4, 256, 6, 1>("v8 u1 warp0 lingers hmul2 EF");
+  run<8, 1, H_NC_NA, 7, 256, 6>("v8 u1 packed atomic (current)");
+  run_tma<13, 512, 0>("tma ring13 512thr 1/SM", 148);
+  run_tma<6, 512, 0>("tma ring6 512thr 2/SM", 296);
+  run_tma<4, 512, 0>("tma ring4 512thr 3/SM", 444);
+  run_tma<6, 256, 0>("tma ring6 256thr 2/SM", 296);
+  run_tma<4, 256, 0>("tma ring4 256thr 3/SM", 444);
+  run_tma<3, 256, 0>("tma ring3 256thr 4/SM", 592);
+  run_tma<2, 256, 0>("tma ring2 256thr 6/SM", 888);
+  run_tma<6, 512, 1>("tma ring6 512thr 2/SM hmul2", 296);
+  run_tma<4, 512, 1>("tma ring4 512thr 3/SM hmul2", 444);
   return 0;
 }
