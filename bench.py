@@ -9,8 +9,8 @@ iteration's hot path for the prompt group(s) this rank owns, on synthetic random
                  pre-generated model output v_i and writing all_latents[:, i+1] in place
   exchange       ONE all_gather_into_tensor of the [3 models x 12] rewards          (N > 1 only)
   advantages     group-relative, 3 reward models, weighted                         (1 launch)
-  policy update  for each of the 4 window steps: log-prob forward, clipped-ratio loss fwd+bwd, log-prob
-                 backward -> grad wrt model output                                 (3 launches each)
+  policy update  for each of the 4 window steps: fused log-prob + clipped-ratio loss forward, fused loss-grad +
+                 log-prob backward -> grad wrt model output                        (2 launches each)
   logging        ONE [4] all_reduce(AVG) of loss/policy/kl/clip_frac               (N > 1 only)
 
 metric  = sampler-step latent GB/s = algorithmic bytes of all sampler/log-prob kernels in the step
@@ -136,6 +136,7 @@ class Workload:
         self.eps = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(WINDOW)]
         self.rewards = torch.randn(N_MODELS, B, device=dev, generator=g)
         self.weights = torch.tensor([1.0, 0.5, 2.0], device=dev)
+        self.stats_rows = torch.zeros(B, 4, device=dev)     # per-sample (loss, policy, kl, clip_frac) accumulators
         self.stats = torch.zeros(4, device=dev)
 
     def noises(self, window):
@@ -159,19 +160,20 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
         gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
         _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
     adv = grpo.compute_group_advantages(rew, B, w.weights)
-    w.stats.zero_()
+    w.stats_rows.zero_()
     grads = []
     for t in window:
         _, _, gv = R.policy_update(v_list[t], traj[:, t], traj[:, t + 1], logps[:, t], adv, w.sig, t, w.cfg, clip_range=CLIP,
                                    adv_clip_max=ADV_CLIP, kl_coeff=KL, gradient_accumulation_steps=GA,
-                                   num_train_timesteps=len(window), stats_accum=w.stats)
+                                   num_train_timesteps=len(window), stats_rows=w.stats_rows)
         grads.append(gv)
+    torch.sum(w.stats_rows, dim=0, out=w.stats)                         # what TR:588-600 accumulate, once per step
     if collectives:
         grpo.reduce_step_stats(w.stats, group)
     return w.stats, logps, grads
 
 
-LAUNCHES_PER_STEP = N_STEPS + 1 + 3 * WINDOW     # our kernels: 25 sampler + 1 advantage + 4 x (fwd, loss, bwd)
+LAUNCHES_PER_STEP = 1 + N_STEPS + 1 + 2 * WINDOW  # our kernels: trajectory seed + 25 sampler + 1 advantage + 4 x (policy fwd, policy bwd)
 
 
 def capture_step(w: Workload, window):
@@ -395,7 +397,7 @@ def run_native(args):
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages + rollout.policy_update (eager)"},
+                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages + rollout.policy_update (eager launches)"},
             "gpu_launches": LAUNCHES_PER_STEP * args.steps,
             "clocks": clk.summary(), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "check": {"loss": loss_host, "e2e_loss": e2e_loss, "logp_mean": float(logps[:, window[0]].mean().item())},

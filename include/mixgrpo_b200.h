@@ -142,6 +142,32 @@ int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, 
                         void* grad_v, int64_t B, int64_t n,
                         const mixgrpo_step_coefs* coefs_host, unsigned flags, void* stream);
 
+/* ---- fused policy update: log-prob + clipped-ratio loss, forward and backward, two launches -------
+ * Replaces, for a batch of B stored transitions, grpo_one_step's operator call (TR:149-168), the loss
+ * (TR:560-583) and loss.backward() down to d/d model_output (TR:585) with no separate loss launch:
+ *   mixgrpo_policy_fwd  writes new log-probs [B]; its per-sample finalizer also adds that sample's
+ *                       (loss, policy_loss, kl_loss, clip_frac) — the reference's B == 1 evaluation — to
+ *                       stats_rows[b][0..3] (nullable).  Rows are summed by the caller when it logs.
+ *   mixgrpo_policy_bwd  evaluates dL/dlogp[b] in place from (new_logp, old_logp, advantages)[b] and
+ *                       writes grad_v (dtype v_dtype).
+ * denom = gradient_accumulation_steps * len(train_timesteps) (TR:576).  family: 0 flow, 1 dance (sde). */
+typedef struct mixgrpo_loss_args {
+  const float* old_logp;     /* [B] device */
+  const float* advantages;   /* [B] device (unclamped; adv_clip_max is applied inside, TR:560-564) */
+  float* stats_rows;         /* [B,4] device, accumulated; may be NULL */
+  double clip_range, adv_clip_max, kl_coeff, denom;
+} mixgrpo_loss_args;
+
+int mixgrpo_policy_fwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                       const float* x_next, int64_t in_bs, float* logp_out, void* workspace,
+                       int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                       const mixgrpo_loss_args* loss, unsigned flags, void* stream);
+
+int mixgrpo_policy_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                       const float* x_next, int64_t in_bs, const float* new_logp,
+                       const mixgrpo_loss_args* loss, void* grad_v, int64_t B, int64_t n,
+                       const mixgrpo_step_coefs* coefs_host, unsigned flags, void* stream);
+
 /* ---- reward -> group-relative advantage -------------------------------------------------------
  * Replaces TR:439-501.  rewards is [n_models, local_B] fp32 (one all-gathered or rank-local
  * matrix), groups are consecutive runs of num_generations samples (TR:444-450).
@@ -175,6 +201,10 @@ int mixgrpo_grpo_loss(const float* new_logp, const float* old_logp, const float*
  *                         for the plain permute).  H, W are the UNPACKED latent height/width. */
 int mixgrpo_pack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W,
                          void* stream);
+/* mixgrpo_cast_rows       (B,n) bf16|f32 contiguous -> fp32 rows with batch stride dst_bs: seeds slot 0 of the
+ *                         fp32 trajectory with the bf16 initial latents (SU:26, the list head `z` that torch.stack
+ *                         promotes at SU:153). */
+int mixgrpo_cast_rows(const void* src, int src_dtype, float* dst, int64_t dst_bs, int64_t B, int64_t n, void* stream);
 int mixgrpo_unpack_latents(const void* src, void* dst, int dtype, int64_t B, int C, int H, int W,
                            float divisor, float shift, void* stream);
 

@@ -22,8 +22,15 @@ class StepCoefs(C.Structure):
     _fields_ = [("two_var", C.c_float), ("log_scale", C.c_float), ("log_norm", C.c_float), ("c", C.c_float * 16)]
 
 
+class LossArgs(C.Structure):
+    """mirror of ``mixgrpo_loss_args`` (include/mixgrpo_b200.h)."""
+    _fields_ = [("old_logp", C.c_void_p), ("advantages", C.c_void_p), ("stats_rows", C.c_void_p),
+                ("clip_range", C.c_double), ("adv_clip_max", C.c_double), ("kl_coeff", C.c_double), ("denom", C.c_double)]
+
+
 _P, _I64, _I, _U, _F, _D = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float, C.c_double
 _CP = C.POINTER(StepCoefs)
+_LP = C.POINTER(LossArgs)
 
 # name -> (restype, argtypes); every symbol include/mixgrpo_b200.h declares
 SIGNATURES = {
@@ -36,6 +43,9 @@ SIGNATURES = {
     "mixgrpo_dance_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _I, _U, _P]),
     "mixgrpo_dpm_step": (_I, [_P, _I, _P, _I64, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P]),
     "mixgrpo_logprob_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _CP, _U, _P]),
+    "mixgrpo_policy_fwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),
+    "mixgrpo_policy_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _LP, _P, _I64, _I64, _CP, _U, _P]),
+    "mixgrpo_cast_rows": (_I, [_P, _I, _P, _I64, _I64, _I64, _P]),
     "mixgrpo_group_advantages": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P, _I64, _P, _P]),
     "mixgrpo_grpo_loss": (_I, [_P, _P, _P, _I64, _D, _D, _D, _D, _P, _P, _P, _P]),
     "mixgrpo_pack_latents": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P]),

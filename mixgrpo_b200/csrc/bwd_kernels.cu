@@ -20,6 +20,7 @@ struct BwdParams {
   void* grad_v;
   long long n, x_bs, in_bs;
   mixgrpo_step_coefs k;
+  LossParams loss;          // fused policy path: grad_logp then holds the NEW log-probs and dL/dlogp is evaluated here
 };
 
 template <int FAM, class VT, bool RND, int VEC>
@@ -33,7 +34,9 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
   ld_stream(p.x + (long long)b * p.x_bs + idx, x);
   ld_stream(p.x_next + (long long)b * p.in_bs + idx, xn);
   // (g/n)/(2 s^2): per-sample scalar, same two divisions autograd performs
-  const float gs = __fdiv_rn(__fdiv_rn(__ldg(p.grad_logp + b), (float)p.n), p.k.two_var);
+  float g_lp = __ldg(p.grad_logp + b);
+  if (p.loss.old_lp) g_lp = loss_terms(g_lp, __ldg(p.loss.old_lp + b), __ldg(p.loss.adv + b), p.loss, 1.f).grad;   // TR:560-585 in place
+  const float gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), p.k.two_var);
 
   if constexpr (FAM == 0) {   // flow, SU:186
 #pragma unroll
@@ -108,16 +111,17 @@ static int bwd_family(const BwdParams& p, int v_dtype, int64_t B, bool vec, bool
 
 using namespace mg;
 
-extern "C" __attribute__((visibility("default"))) int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
-                                   const float* x_next, int64_t in_bs, const float* grad_logp, void* grad_v,
-                                   int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, unsigned flags,
-                                   void* stream) {
+static int logprob_bwd_impl(int family, const void* v, int v_dtype, const float* x, int64_t x_bs, const float* x_next,
+                            int64_t in_bs, const float* grad_logp, void* grad_v, int64_t B, int64_t n,
+                            const mixgrpo_step_coefs* coefs_host, const mixgrpo_loss_args* loss, unsigned flags, void* stream) {
   if (!v || !x || !x_next || !grad_logp || !grad_v || !coefs_host || B <= 0 || B > 65535 || n <= 0) return MIXGRPO_EINVAL;
   if (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) return MIXGRPO_EINVAL;
   if (family != 0 && family != 1) return MIXGRPO_EINVAL;
   BwdParams p;
   p.v = v; p.x = x; p.x_next = x_next; p.grad_logp = grad_logp; p.grad_v = grad_v;
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.k = *coefs_host;
+  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  if (loss) p.loss = make_loss_params(loss->old_logp, loss->advantages, nullptr, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
   auto al = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   const size_t va = v_dtype == MIXGRPO_BF16 ? 16 : 32;
   const bool vec = (n % kVec == 0) && (x_bs % kVec == 0) && (in_bs % kVec == 0) && al(v, va) && al(grad_v, va) &&
@@ -125,4 +129,21 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_logprob_bwd(int fa
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return family == 0 ? bwd_family<0>(p, v_dtype, B, vec, rnd, st) : bwd_family<1>(p, v_dtype, B, vec, rnd, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                                   const float* x_next, int64_t in_bs, const float* grad_logp, void* grad_v,
+                                   int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, unsigned flags,
+                                   void* stream) {
+  return logprob_bwd_impl(family, v, v_dtype, x, x_bs, x_next, in_bs, grad_logp, grad_v, B, n, coefs_host, nullptr, flags, stream);
+}
+
+// Fused policy-update backward: dL/dlogp[b] is evaluated in place from (new_logp, old_logp, advantage)[b] — the
+// loss never exists as a separate launch — then the same closed-form chain as mixgrpo_logprob_bwd.
+extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                                  const float* x_next, int64_t in_bs, const float* new_logp, const mixgrpo_loss_args* loss,
+                                  void* grad_v, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, unsigned flags,
+                                  void* stream) {
+  if (!loss || !loss->old_logp || !loss->advantages) return MIXGRPO_EINVAL;
+  return logprob_bwd_impl(family, v, v_dtype, x, x_bs, x_next, in_bs, new_logp, grad_v, B, n, coefs_host, loss, flags, stream);
 }

@@ -107,5 +107,52 @@ __device__ __forceinline__ float block_sum(float v, float* s_warp /* [kThreads/3
   return t;
 }
 
+// ---------------------------------------------------------------- clipped-ratio GRPO loss, one sample
+// TR:560-583 for ONE log-prob (TR = fastvideo/train_grpo_flux.py).  Shared by the batch loss kernel and by the
+// fused policy path, where the forward log-prob kernel's finalizer and every CTA of the backward kernel
+// evaluate it in place (no loss launch, no host sync).
+struct LossParams {
+  const float* old_lp;     // [B]   (fused path only)
+  const float* adv;        // [B]
+  float* rows;             // [B,4] running (loss, policy, kl, clip_frac) per sample, or nullptr
+  float clip, lo, hi, amax, klc, denom;
+};
+
+struct LossTerms {
+  float policy_num;        // max(-A r, -A clamp(r))           -> mean / denom = policy loss
+  float kl_num;            // (new - old)^2                    -> 0.5 * mean / denom = kl loss
+  float clip;              // |r - 1| > clip_range ? 1 : 0
+  float grad;              // d loss / d new_logp  (includes the 1/B of the batch mean via inv_b)
+};
+
+__host__ inline LossParams make_loss_params(const float* old_lp, const float* adv, float* rows, double clip_range,
+                                            double adv_clip_max, double kl_coeff, double denom) {
+  LossParams q;
+  q.old_lp = old_lp; q.adv = adv; q.rows = rows;
+  // python scalars are narrowed to fp32 exactly where torch narrows them; 1 -/+ clip is formed in double (TR:571-572)
+  q.clip = (float)clip_range; q.lo = (float)(1.0 - clip_range); q.hi = (float)(1.0 + clip_range);
+  q.amax = (float)adv_clip_max; q.klc = (float)kl_coeff; q.denom = (float)denom;
+  return q;
+}
+
+__device__ __forceinline__ LossTerms loss_terms(float new_lp, float old_lp, float adv, const LossParams& q, float inv_b) {
+  LossTerms t;
+  const float a = fminf(fmaxf(adv, -q.amax), q.amax);              // TR:560-564
+  const float lr = __fsub_rn(new_lp, old_lp);
+  const float r = expf(lr);                                        // TR:566
+  const float rc = fminf(fmaxf(r, q.lo), q.hi);
+  const float un = __fmul_rn(-a, r), cl = __fmul_rn(-a, rc);        // TR:568-573
+  t.policy_num = fmaxf(un, cl);
+  t.clip = (fabsf(__fsub_rn(r, 1.f)) > q.clip) ? 1.f : 0.f;        // TR:574
+  t.kl_num = __fmul_rn(lr, lr);                                    // TR:580
+  // torch.maximum splits the gradient 1/2 + 1/2 on ties; clamp passes gradient on [lo, hi] inclusive
+  const float inside = (r >= q.lo && r <= q.hi) ? 1.f : 0.f;
+  float dpl_dr;
+  if (un > cl) dpl_dr = -a;
+  else if (un < cl) dpl_dr = -a * inside;
+  else dpl_dr = 0.5f * (-a) + 0.5f * (-a) * inside;
+  t.grad = dpl_dr * r * inv_b / q.denom + q.klc * lr * inv_b / q.denom;
+  return t;
+}
 
 }  // namespace mg

@@ -67,6 +67,40 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_unpack_latents(con
   return mg::launch_pack<false>(src, dst, dtype, B, C, H, W, divisor, shift, reinterpret_cast<cudaStream_t>(stream));
 }
 
+namespace mg {
+template <class T, bool VECTOR>
+__global__ void __launch_bounds__(256) cast_rows_kernel(const T* __restrict__ src, float* __restrict__ dst, long long dst_bs, long long n) {
+  const int b = blockIdx.y;
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * (VECTOR ? kVec : 1);
+  if (i >= n) return;
+  if constexpr (VECTOR) {
+    float r[kVec];
+    ld_stream(src + (long long)b * n + i, r);
+    st_stream(dst + (long long)b * dst_bs + i, r);
+  } else {
+    dst[(long long)b * dst_bs + i] = (float)src[(long long)b * n + i];
+  }
+}
+}  // namespace mg
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_cast_rows(const void* src, int src_dtype, float* dst, int64_t dst_bs, int64_t B, int64_t n,
+                                                                       void* stream) {
+  if (!src || !dst || B <= 0 || B > 65535 || n <= 0 || (src_dtype != MIXGRPO_F32 && src_dtype != MIXGRPO_BF16)) return MIXGRPO_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uintptr_t s = reinterpret_cast<uintptr_t>(src), d = reinterpret_cast<uintptr_t>(dst);
+  const bool vec = (n % mg::kVec == 0) && (dst_bs % mg::kVec == 0) && (d % 32 == 0) && (s % (src_dtype == MIXGRPO_BF16 ? 16 : 32) == 0);
+  const long long per = 256LL * (vec ? mg::kVec : 1);
+  dim3 grid((unsigned)((n + per - 1) / per), (unsigned)B);
+  if (src_dtype == MIXGRPO_BF16) {
+    if (vec) mg::cast_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, dst_bs, n);
+    else mg::cast_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, dst_bs, n);
+  } else {
+    if (vec) mg::cast_rows_kernel<float, true><<<grid, 256, 0, st>>>((const float*)src, dst, dst_bs, n);
+    else mg::cast_rows_kernel<float, false><<<grid, 256, 0, st>>>((const float*)src, dst, dst_bs, n);
+  }
+  return (int)cudaGetLastError();
+}
+
 extern "C" __attribute__((visibility("default"))) int mixgrpo_abi_version(void) { return MIXGRPO_ABI_VERSION; }
 
 #define MG_STR2(x) #x

@@ -37,6 +37,7 @@ struct StepParams {
   long long n, x_bs, in_bs, out_bs;
   int B, tiles;
   mixgrpo_step_coefs k;
+  LossParams loss;          // fused policy path (SRC_GIVEN only): old log-probs / advantages / stats rows, or nullptrs
 };
 
 // ------------------------------------------------------------------ per-tile arithmetic
@@ -264,8 +265,23 @@ step_kernel(const __grid_constant__ StepParams p) {
       float q = (float)((double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0));
       if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) q = __int_as_float(0x7fc00000);
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
-      p.logp_out[b] = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
+      const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
+      p.logp_out[b] = lp;
       p.acc[b] = 0ull;
+      if constexpr (SRC == MIXGRPO_SRC_GIVEN) {
+        // fused policy path: the sample's clipped-ratio loss terms (TR:560-583, one sample = the reference's B == 1)
+        // are added to its own stats row by this single thread — ordered across launches, no extra kernel
+        if (p.loss.rows) {
+          const LossTerms t = loss_terms(lp, p.loss.old_lp[b], p.loss.adv[b], p.loss, 1.f);
+          const float policy = __fdiv_rn(t.policy_num, p.loss.denom);
+          const float kl = __fdiv_rn(__fmul_rn(0.5f, t.kl_num), p.loss.denom);
+          float* row = p.loss.rows + 4 * (long long)b;
+          row[0] += __fadd_rn(policy, __fmul_rn(p.loss.klc, kl));
+          row[1] += policy;
+          row[2] += kl;
+          row[3] += t.clip;
+        }
+      }
     }
   }
 }
@@ -335,6 +351,7 @@ static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, con
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
   p.B = (int)B; p.tiles = 0; p.k = *k;
+  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
 }
 
 // 256-bit path needs 32-B aligned fp32 streams, 16-B aligned bf16 streams and n, strides % 8 == 0.
@@ -430,4 +447,32 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_dpm_step(const voi
     case 2: return dpm_dispatch<2>(p, v_dtype, B, src, vec, rnd, st);
     default: return dpm_dispatch<3>(p, v_dtype, B, src, vec, rnd, st);
   }
+}
+
+// Fused policy-update forward: log p(x_next | x, v) for the stored transition (TR:149-168 via grpo_one_step) AND the
+// per-sample clipped-ratio loss terms (TR:560-583) accumulated into stats_rows — one launch, nothing else.
+extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                                  const float* x_next, int64_t in_bs, float* logp_out, void* workspace, int64_t workspace_bytes,
+                                  int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, const mixgrpo_loss_args* loss,
+                                  unsigned flags, void* stream) {
+  int err = 0;
+  if (!coefs_host || !logp_out || !x_next || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err))
+    return err ? err : MIXGRPO_EINVAL;
+  if (family != kFlow && family != kDance) return MIXGRPO_EINVAL;
+  if (loss && (!loss->old_logp || !loss->advantages)) return MIXGRPO_EINVAL;
+  StepParams p;
+  fill(p, v, x, x_bs, nullptr, x_next, in_bs, nullptr, nullptr, nullptr, n, nullptr, nullptr, logp_out, workspace, B, n, coefs_host);
+  if (loss) p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
+  const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
+  const int src = MIXGRPO_SRC_GIVEN;
+  if (family == kFlow) {
+    if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
+    if (rnd) return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, true, false>(p, B, src, vec, st);
+    return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, false, false>(p, B, src, vec, st);
+  }
+  if (v_dtype == MIXGRPO_F32) return pick_src<kDance, float, float, 1, false, true>(p, B, src, vec, st);
+  if (rnd) return pick_src<kDance, __nv_bfloat16, float, 1, true, true>(p, B, src, vec, st);
+  return pick_src<kDance, __nv_bfloat16, float, 1, false, true>(p, B, src, vec, st);
 }

@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import BF16, F32, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, StepCoefs
+from ._cabi import BF16, F32, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, LossArgs, StepCoefs
 
 FLOW, DANCE, DPM = 0, 1, 2
 
@@ -185,6 +185,97 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
     _cabi.check(rc, "logprob_bwd")
     launch_count += 1
     return grad_v
+
+
+def _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, device):
+    keep = []
+    def vec(t, name):
+        _require_cuda(t, name)
+        t = t.detach().to(torch.float32).contiguous().view(-1)
+        if t.numel() != B:
+            raise ValueError(f"mixgrpo_b200: `{name}` must have one entry per sample")
+        keep.append(t)
+        return t.data_ptr()
+    la = LossArgs()
+    la.old_logp, la.advantages = vec(old_logp, "old_log_probs"), vec(advantages, "advantages")
+    la.stats_rows = None
+    if stats_rows is not None:
+        if stats_rows.dtype != torch.float32 or tuple(stats_rows.shape) != (B, 4) or not stats_rows.is_contiguous() or stats_rows.device != device:
+            raise ValueError("mixgrpo_b200: stats_rows must be a contiguous fp32 [B, 4] tensor on the same device")
+        la.stats_rows = stats_rows.data_ptr()
+    la.clip_range, la.adv_clip_max, la.kl_coeff, la.denom = float(clip_range), float(adv_clip_max), float(kl_coeff), float(denom)
+    return la, keep
+
+
+def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, coefs: StepCoefs, old_logp: torch.Tensor,
+                   advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float, denom: float,
+                   stats_rows: Optional[torch.Tensor] = None, round_like_torch: bool = False,
+                   out_logp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused policy-update forward (mixgrpo_policy_fwd): new log-probs [B]; per-sample loss terms += stats_rows."""
+    global launch_count
+    lib = _cabi.lib()
+    for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample")):
+        _require_cuda(t, nm)
+    vd = _dtype_code(v, "model_output")
+    v = v if v.is_contiguous() else v.contiguous()
+    B, n, dev = v.shape[0], v[0].numel(), v.device
+    x, x_bs = _rows(x.to(torch.float32), "latents")
+    x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
+    la, keep = _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, dev)
+    logp = out_logp if out_logp is not None else torch.empty((B,), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, B, n)
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    with torch.cuda.device(dev):
+        rc = lib.mixgrpo_policy_fwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, logp.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), B, n, C.byref(coefs), C.byref(la), flags, _stream_ptr(dev))
+    _cabi.check(rc, "policy_fwd")
+    launch_count += 1
+    del keep
+    return logp
+
+
+def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, new_logp: torch.Tensor, coefs: StepCoefs,
+                    old_logp: torch.Tensor, advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float,
+                    denom: float, round_like_torch: bool = False) -> torch.Tensor:
+    """Fused policy-update backward (mixgrpo_policy_bwd): d loss / d model_output, dtype = model_output.dtype."""
+    global launch_count
+    lib = _cabi.lib()
+    for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (new_logp, "new_log_probs")):
+        _require_cuda(t, nm)
+    vd = _dtype_code(v, "model_output")
+    v = v if v.is_contiguous() else v.contiguous()
+    B, n, dev = v.shape[0], v[0].numel(), v.device
+    x, x_bs = _rows(x.to(torch.float32), "latents")
+    x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
+    nl = new_logp.detach().to(torch.float32).contiguous().view(-1)
+    la, keep = _loss_args(old_logp, advantages, None, clip_range, adv_clip_max, kl_coeff, denom, B, dev)
+    grad_v = torch.empty_like(v)
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    with torch.cuda.device(dev):
+        rc = lib.mixgrpo_policy_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, nl.data_ptr(), C.byref(la),
+                                    grad_v.data_ptr(), B, n, C.byref(coefs), flags, _stream_ptr(dev))
+    _cabi.check(rc, "policy_bwd")
+    launch_count += 1
+    del keep
+    return grad_v
+
+
+def cast_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[b] = float32(src[b]) for a (B, ...) bf16|f32 contiguous ``src`` and an fp32 ``dst`` view whose per-sample
+    block is contiguous (e.g. ``all_latents[:, 0]``): seeds the trajectory buffer (SU:26, SU:153)."""
+    global launch_count
+    _require_cuda(src, "src")
+    _require_cuda(dst, "dst")
+    code = _dtype_code(src, "src")
+    src = src if src.is_contiguous() else src.contiguous()
+    if dst.dtype != torch.float32 or dst.shape != src.shape or not dst[0].is_contiguous():
+        raise ValueError("mixgrpo_b200: dst must be fp32, same shape, contiguous per sample")
+    B, n = src.shape[0], src[0].numel()
+    with torch.cuda.device(src.device):
+        rc = _cabi.lib().mixgrpo_cast_rows(src.data_ptr(), code, dst.data_ptr(), dst.stride(0) if B > 1 else n, B, n, _stream_ptr(src.device))
+    _cabi.check(rc, "cast_rows")
+    launch_count += 1
+    return dst
 
 
 def group_advantages(rewards: torch.Tensor, weights: Optional[torch.Tensor], num_generations: int, trim_size: int = 0,

@@ -7,8 +7,8 @@ with ~15 scalar kernels, 4 all-reduces and 5 ``.item()`` syncs each (TR:536-600)
 * ``rollout``            — the whole group in ONE batch: per step one model call + one fused kernel that
                            reads ``all_latents[:, i]`` and writes ``all_latents[:, i+1]`` in place.
 * ``make_samples``       — TR:400-415 (views, no copies).
-* ``policy_update``      — log-prob forward → loss fwd+bwd → log-prob backward: three launches, zero host
-                           syncs; returns ``grad_model_output`` for ``pred.backward(grad)``.
+* ``policy_update``      — fused log-prob + loss forward, fused loss-grad + log-prob backward: two launches, zero
+                           host syncs; returns ``grad_model_output`` for ``pred.backward(grad)``.
 * ``balance_pos_neg`` / ``shuffle_timesteps`` — sample bookkeeping of TR:503-532 and
                            fastvideo/models/reward_model/utils.py:18-48.
 """
@@ -82,7 +82,7 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
     n_steps = sigmas.size(0) - 1
     B, dev = z.shape[0], z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
-    traj[:, 0].copy_(z)
+    _ops.cast_rows(z, traj[:, 0])
     logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
     host_sig = _coefs.host_schedule(sigmas).tolist()
     x0 = None
@@ -176,10 +176,11 @@ def balance_pos_neg(samples: List[dict], use_random: bool = False, rng: Optional
 def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Tensor, old_log_probs: torch.Tensor,
                   advantages: torch.Tensor, sigmas: torch.Tensor, index: int, cfg: SamplerConfig, *, clip_range: float,
                   adv_clip_max: float, kl_coeff: float, gradient_accumulation_steps: int, num_train_timesteps: int,
-                  stats_accum: Optional[torch.Tensor] = None, per_sample_loss: bool = True):
+                  stats_rows: Optional[torch.Tensor] = None):
     """One (samples, window step) policy update, TR:542-585 without autograd: given the model output ``v`` for
-    the stored ``latents`` it returns ``(stats[4], new_log_probs [B], grad_v)`` where ``grad_v`` is
-    dloss/dv — hand it to ``v.backward(grad_v)`` to continue into the DiT.  Three kernel launches, no sync."""
+    the stored ``latents`` it returns ``(stats_rows, new_log_probs [B], grad_v)`` where ``grad_v`` is dloss/dv — hand it
+    to ``v.backward(grad_v)`` to continue into the DiT.  ``stats_rows`` ([B,4] fp32, optional) accumulates each sample's
+    (loss, policy_loss, kl_loss, clip_frac); ``stats_rows.sum(0)`` is what TR:588-600 adds up.  Two launches, no sync."""
     mode = _mode(cfg.rounding)
     bf16_v = v.dtype == torch.bfloat16
     rnd = bf16_v and mode != "fp32"
@@ -188,15 +189,13 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     else:
         fam, (k, _) = _ops.DANCE, _coefs.dance(sigmas, index, cfg.eta, mode, bf16_v)
     vd = v.detach()
-    _, _, new_lp, _ = _ops.fused_step(fam, vd, latents, k, src=SRC_GIVEN, x_next=next_latents, want_x0=False,
-                                      sde_solver=True, round_like_torch=rnd)
-    # The reference evaluates the loss one sample at a time (B == 1 per call, TR:536-585) and lets autograd
-    # accumulate: sum_i loss_i / (GA*T).  A batch of B samples in one launch is the same thing with the mean's
-    # 1/B folded into the denominator; stats[0..2] are then the SUMS over the batch (what TR:588-596 add up).
+    # The reference evaluates the loss one sample at a time (B == 1 per call, TR:536-585) and lets autograd accumulate
+    # sum_i loss_i / (GA*T); the fused kernels do exactly that per sample: forward = log-prob + loss terms into the
+    # sample's stats row, backward = dL/dlogp evaluated in place + closed-form chain.  Two launches, no loss kernel.
     denom = float(gradient_accumulation_steps * num_train_timesteps)
-    if per_sample_loss:
-        denom /= v.shape[0]
-    stats, g_lp = _ops.grpo_loss_fwd_bwd(new_lp, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff, denom,
-                                         want_grad=True, stats_accum=stats_accum)
-    grad_v = _ops.logprob_backward(fam, vd, latents, next_latents, g_lp, k, rnd)
-    return stats, new_lp, grad_v
+    new_lp = _ops.policy_forward(fam, vd, latents, next_latents, k, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
+                                 denom, stats_rows=stats_rows, round_like_torch=rnd)
+    grad_v = _ops.policy_backward(fam, vd, latents, next_latents, new_lp, k, old_log_probs, advantages, clip_range, adv_clip_max,
+                                  kl_coeff, denom, round_like_torch=rnd)
+    return stats_rows, new_lp, grad_v
+

@@ -310,7 +310,7 @@ def run_sample_step(
     B = z.shape[0]
     dev = z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
-    traj[:, 0].copy_(z)
+    _ops.cast_rows(z, traj[:, 0])
     logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)   # step-major so each kernel writes a row
     mode = _mode(rounding)
     host_sig = _coefs.host_schedule(sigma_schedule)

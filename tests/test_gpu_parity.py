@@ -305,3 +305,59 @@ def test_errors_and_no_cpu_fallback():
     d = _dev()
     with pytest.raises(ValueError, match="Cannot pass both generator and prev_sample"):
         su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, 0, xn.to(d), generator=torch.Generator())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("flow", [True, False])
+def test_fused_policy_update_vs_oracle_autograd(dtype, flow):
+    """rollout.policy_update (fused log-prob+loss forward, fused loss-grad+log-prob backward: two launches) against
+    the oracle evaluated the reference's way: one sample at a time, autograd through step + loss (TR:536-585)."""
+    from mixgrpo_b200 import rollout as R
+    d = _dev()
+    Bn, idx, T, GA = 6, 8, 4, 3
+    x, v, eps, _ = _inputs(Bn, 64, dtype, seed=55)
+    nz = eps if flow else eps.float()
+    with torch.no_grad():
+        if flow:
+            xn, _, old_lp, _, _ = O.flow_step(v, x, ETA, SIG, idx, None, nz, False)
+        else:
+            xn, _, old_lp = O.dance_step(v, x, ETA, SIG, idx, None, nz, True, True)
+    v_new = (v.float() + 0.02 * torch.randn(v.shape, generator=torch.Generator().manual_seed(3))).to(dtype)   # the policy moved a little
+    adv = torch.tensor([1.3, -0.4, 9.0, -7.5, 0.2, 0.0])
+    clip, amax, klc = 1e-4, 5.0, 0.01
+    cfg = R.SamplerConfig(flow_grpo_sampling=flow, rounding="ref_cpu")
+    rows = torch.zeros(Bn, 4, device=d)
+    _, new_lp, gv = R.policy_update(v_new.to(d), x.to(d), xn.to(d), old_lp.to(d), adv.to(d), SIG, idx, cfg, clip_range=clip, adv_clip_max=amax,
+                                    kl_coeff=klc, gradient_accumulation_steps=GA, num_train_timesteps=T, stats_rows=rows)
+    vc = v_new.clone().requires_grad_(True)
+    ref_rows = torch.zeros(Bn, 4)
+    lps = []
+    for i in range(Bn):                                          # the reference's per-sample loop
+        if flow:
+            lp = O.flow_step(vc[i:i + 1], x[i:i + 1], ETA, SIG, idx, xn[i:i + 1])[2]
+        else:
+            lp = O.dance_step(vc[i:i + 1], x[i:i + 1], ETA, SIG, idx, xn[i:i + 1], None, True, True)[2]
+        out = GO.grpo_loss(lp, old_lp[i:i + 1], adv[i:i + 1], clip, amax, klc, GA, T)
+        out[0].backward()
+        ref_rows[i] = torch.stack([o.detach() for o in out])
+        lps.append(lp.detach())
+    assert torch.allclose(new_lp.cpu(), torch.cat(lps), rtol=1e-5, atol=0)
+    assert torch.allclose(rows.cpu(), ref_rows, rtol=2e-4, atol=1e-7), (rows.cpu() - ref_rows).abs().max()
+    assert gv.dtype == dtype
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert _rel(gv.float().cpu(), vc.grad.float()) < tol
+    # a second call accumulates into the same rows
+    R.policy_update(v_new.to(d), x.to(d), xn.to(d), old_lp.to(d), adv.to(d), SIG, idx, cfg, clip_range=clip, adv_clip_max=amax,
+                    kl_coeff=klc, gradient_accumulation_steps=GA, num_train_timesteps=T, stats_rows=rows)
+    assert torch.allclose(rows.cpu(), 2 * ref_rows, rtol=2e-4, atol=2e-7)
+
+
+def test_cast_rows_seeds_trajectory_slot():
+    from mixgrpo_b200 import ops
+    d = _dev()
+    for shape in [(3, 128, 64), (2, 7, 5)]:
+        z = torch.randn(*shape).bfloat16()
+        traj = torch.full((shape[0], 3) + shape[1:], -1.0, device=d)
+        ops.cast_rows(z.to(d), traj[:, 0])
+        assert torch.equal(traj[:, 0].cpu(), z.float())
+        assert torch.equal(traj[:, 1:].cpu(), torch.full((shape[0], 2) + shape[1:], -1.0))
