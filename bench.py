@@ -327,6 +327,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import mixgrpo_b200
     from mixgrpo_b200 import ops
@@ -339,12 +340,22 @@ def run_native(args):
 
     graph, (stats, logps, _) = capture_step(w, window)
 
+    # The path's two tiny collectives (reward all-gather, stats all-reduce) feed logging only in the reference's
+    # group mode (TR:427-437, TR:586-600), so they run on a side stream: ordered after the step that produced their
+    # inputs, waited for before the next step overwrites them, and inside the timed region.
+    main_stream = torch.cuda.current_stream(dev)
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def step():
+        if world > 1:
+            main_stream.wait_stream(comm_stream)
         graph.replay()
-        if world > 1:                                                   # the path's two tiny collectives, outside the graph
+        if world > 1:
             from mixgrpo_b200 import grpo
-            grpo.gather_rewards(w.rewards)
-            grpo.reduce_step_stats(w.stats)
+            comm_stream.wait_stream(main_stream)
+            with torch.cuda.stream(comm_stream):
+                grpo.gather_rewards(w.rewards)
+                grpo.reduce_step_stats(w.stats)
 
     for _ in range(args.warmup):
         step()
@@ -359,6 +370,8 @@ def run_native(args):
         a.record()
         for _ in range(args.steps):
             step()
+        if world > 1:
+            main_stream.wait_stream(comm_stream)      # the last step's collectives end inside the timed region
         b.record()
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
@@ -455,6 +468,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the arm uses all host cores
     cpu = cpu_reference_step(args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "sampler-step latent GB/s", "value": cpu["value"], "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cpu["s_per_step"] * 1e3, 2), "higher_is_better": True,
