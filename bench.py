@@ -243,6 +243,29 @@ def measure_roofline(dev, peak_gbs, peak_kind):
             us = a.elapsed_time(b) * 1e3 / (reps * ns)
         res[kind] = {"us_per_launch": round(us, 3), "bytes_per_elem": BYTES[kind], "GBps": round(e * BYTES[kind] / us / 1e3, 1)}
         del gr
+    # A/B: the headline kernel without programmatic dependent launch (each launch waits for the previous one to drain)
+    from mixgrpo_b200 import _cabi
+    _cabi.lib().mixgrpo_set_tuning(1, 0)
+    with torch.cuda.stream(s):
+        for i in range(ns):
+            run("sde_x0", i)
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for i in range(ns):
+                run("sde_x0", i)
+        for _ in range(3):
+            gr.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        for _ in range(20):
+            gr.replay()
+        b.record(s)
+        b.synchronize()
+        res["sde_x0_no_pdl"] = {"us_per_launch": round(a.elapsed_time(b) * 1e3 / (20 * ns), 3), "bytes_per_elem": 16,
+                                "GBps": round(e * 16 / (a.elapsed_time(b) * 1e3 / (20 * ns)) / 1e3, 1)}
+    _cabi.lib().mixgrpo_set_tuning(1, 1)
+    del gr
     top = res["sde_x0"]
     roof = {"bound": "hbm", "kernel": "mg::step_kernel<flow, bf16, SRC_NOISE> (fused SDE step + log-prob -> prev_sample, pred_x0, log_prob)",
             "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",

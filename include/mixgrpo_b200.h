@@ -41,6 +41,9 @@ enum {
 
 /* flags */
 #define MIXGRPO_FLAG_ROUND_LIKE_TORCH 1u /* reproduce torch's bf16 type-promotion roundings */
+#define MIXGRPO_FLAG_PDL_EARLY_LOADS  2u /* backward only: v / x / x_next were NOT written by the kernel launched
+                                            immediately before on this stream (e.g. right after mixgrpo_policy_fwd):
+                                            their loads may overlap that kernel's tail (programmatic dependent launch) */
 
 /* error codes */
 #define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
@@ -88,7 +91,7 @@ int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
 /* ABI / build introspection. */
 int mixgrpo_abi_version(void);
 const char* mixgrpo_build_info(void);          /* e.g. "sm_100a nvcc 12.9 ..." (static string) */
-int mixgrpo_set_tuning(int key, int value);    /* bench-only knobs; returns previous value or <0 */
+int mixgrpo_set_tuning(int key, int value);    /* bench-only knobs (0: max CTAs/sample, 1: PDL on/off); returns previous value or <0 */
 const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGetErrorString for >0) */
 
 /* ---- fused sampler step + Gaussian transition log-prob ---------------------------------------

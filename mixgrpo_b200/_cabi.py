@@ -14,6 +14,7 @@ from . import _build
 F32, BF16 = 0, 1
 SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC = 0, 1, 2
 FLAG_ROUND_LIKE_TORCH = 1
+FLAG_PDL_EARLY_LOADS = 2
 ABI_VERSION = 1
 
 

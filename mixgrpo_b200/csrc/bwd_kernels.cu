@@ -23,16 +23,24 @@ struct BwdParams {
   LossParams loss;          // fused policy path: grad_logp then holds the NEW log-probs and dL/dlogp is evaluated here
 };
 
-template <int FAM, class VT, bool RND, int VEC>
+// EARLY (MIXGRPO_FLAG_PDL_EARLY_LOADS): the caller guarantees that v / x / x_next were not written by the kernel
+// launched immediately before this one (true right after mixgrpo_policy_fwd, which only writes log-probs), so their
+// loads are issued BEFORE griddepcontrol.wait and overlap the predecessor's tail; only dL/dlogp is read after it.
+template <int FAM, class VT, bool RND, int VEC, bool EARLY>
 __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_constant__ BwdParams p) {
+  if constexpr (!EARLY) pdl_prologue();
   const int b = blockIdx.y;
   const long long idx = ((long long)blockIdx.x * kThreads + threadIdx.x) * VEC;
-  if (idx >= p.n) return;
+  const bool active = idx < p.n;
   const float* c = p.k.c;
   float v[VEC], x[VEC], xn[VEC], t[VEC], mu[VEC], x0[VEC], g[VEC];
-  ld_stream(reinterpret_cast<const VT*>(p.v) + (long long)b * p.n + idx, v);
-  ld_stream(p.x + (long long)b * p.x_bs + idx, x);
-  ld_stream(p.x_next + (long long)b * p.in_bs + idx, xn);
+  if (active) {
+    ld_stream(reinterpret_cast<const VT*>(p.v) + (long long)b * p.n + idx, v);
+    ld_stream(p.x + (long long)b * p.x_bs + idx, x);
+    ld_stream(p.x_next + (long long)b * p.in_bs + idx, xn);
+  }
+  if constexpr (EARLY) pdl_prologue();
+  if (!active) return;
   // (g/n)/(2 s^2): per-sample scalar, same two divisions autograd performs
   float g_lp = __ldg(p.grad_logp + b);
   if (p.loss.old_lp) g_lp = loss_terms(g_lp, __ldg(p.loss.old_lp + b), __ldg(p.loss.adv + b), p.loss, 1.f).grad;   // TR:560-585 in place
@@ -89,22 +97,23 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
 }
 
 template <int FAM, class VT, bool RND>
-static int launch_bwd(const BwdParams& p, int64_t B, bool vec, cudaStream_t st) {
+static int launch_bwd(const BwdParams& p, int64_t B, bool vec, bool early, cudaStream_t st) {
   if (vec) {
     dim3 grid((unsigned)((p.n + (long long)kThreads * kVec - 1) / ((long long)kThreads * kVec)), (unsigned)B);
-    logprob_bwd_kernel<FAM, VT, RND, kVec><<<grid, kThreads, 0, st>>>(p);
+    if (early) launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, true>, grid, kThreads, 0, st, p);
+    else launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, false>, grid, kThreads, 0, st, p);
   } else {
     dim3 grid((unsigned)((p.n + kThreads - 1) / kThreads), (unsigned)B);
-    logprob_bwd_kernel<FAM, VT, RND, 1><<<grid, kThreads, 0, st>>>(p);
+    launch_pdl(logprob_bwd_kernel<FAM, VT, RND, 1, false>, grid, kThreads, 0, st, p);
   }
   return (int)cudaGetLastError();
 }
 
 template <int FAM>
-static int bwd_family(const BwdParams& p, int v_dtype, int64_t B, bool vec, bool rnd, cudaStream_t st) {
-  if (v_dtype == MIXGRPO_F32) return launch_bwd<FAM, float, false>(p, B, vec, st);
-  if (rnd) return launch_bwd<FAM, __nv_bfloat16, true>(p, B, vec, st);
-  return launch_bwd<FAM, __nv_bfloat16, false>(p, B, vec, st);
+static int bwd_family(const BwdParams& p, int v_dtype, int64_t B, bool vec, bool rnd, bool early, cudaStream_t st) {
+  if (v_dtype == MIXGRPO_F32) return launch_bwd<FAM, float, false>(p, B, vec, early, st);
+  if (rnd) return launch_bwd<FAM, __nv_bfloat16, true>(p, B, vec, early, st);
+  return launch_bwd<FAM, __nv_bfloat16, false>(p, B, vec, early, st);
 }
 
 }  // namespace mg
@@ -128,7 +137,8 @@ static int logprob_bwd_impl(int family, const void* v, int v_dtype, const float*
                    al(x, 32) && al(x_next, 32);
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return family == 0 ? bwd_family<0>(p, v_dtype, B, vec, rnd, st) : bwd_family<1>(p, v_dtype, B, vec, rnd, st);
+  const bool early = (flags & MIXGRPO_FLAG_PDL_EARLY_LOADS) != 0;
+  return family == 0 ? bwd_family<0>(p, v_dtype, B, vec, rnd, early, st) : bwd_family<1>(p, v_dtype, B, vec, rnd, early, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,

@@ -85,6 +85,33 @@ __device__ __forceinline__ void round_like_torch(float (&r)[N]) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+//   griddepcontrol.wait              -> the previous grid on the stream has completed and its writes are visible
+//   griddepcontrol.launch_dependents -> the NEXT grid may start filling SMs as this grid's CTAs retire
+// so in a chain of our launches (25 sampler steps, policy forward -> backward) the next kernel's launch latency and
+// ramp-up overlap this kernel's tail instead of following it.  The trigger comes AFTER the wait on purpose: a dependent
+// can then only start once everything two launches back has completed, which is what makes "early loads" (inputs that
+// the immediately preceding kernel does not write, MIXGRPO_FLAG_PDL_EARLY_LOADS) safe.  After a non-PDL kernel (torch,
+// cuBLAS) the attribute is inert and ordering is the ordinary stream order.  Measured: -0.4 us per chained launch,
+// -1.1 us with early loads (profiles/r01_design_space.md).
+extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_kernels.cu
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_wait(); pdl_launch_dependents(); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- deterministic reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

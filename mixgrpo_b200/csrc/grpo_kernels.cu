@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kAdvThreads) group_adv_kernel(const float* __r
                                                                const float* __restrict__ weights, int n_models,
                                                                long long local_B, int G, int trim,
                                                                float* __restrict__ adv) {
+  pdl_prologue();
   extern __shared__ float s_r[];            // [n_models][G] rewards, then [n_models][2] (mean, std+1e-8)
   float* s_stat = s_r + (size_t)n_models * G;
   const int g = blockIdx.x;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kAdvThreads) group_adv_kernel(const float* __r
 __global__ void __launch_bounds__(256) global_adv_kernel(const float* __restrict__ rewards, long long local_B,
                                                         const float* __restrict__ stat, long long n_stat,
                                                         float* __restrict__ adv) {
+  pdl_prologue();
   __shared__ double s_red[8];
   __shared__ float s_stat[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(THREADS) grpo_loss_kernel(const float* __restr
                                                            const float* __restrict__ adv, long long B, LossParams q,
                                                            float* __restrict__ stats, float* __restrict__ grad,
                                                            float* __restrict__ accum) {
+  pdl_prologue();
   __shared__ float s_warp[3][THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float s_pol = 0.f, s_kl = 0.f, s_cf = 0.f;
@@ -161,7 +164,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_group_advantages(c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!use_group) {
     if (n_models != 1 || !stat_rewards || n_stat <= 0) return MIXGRPO_EINVAL;   // TR:495-496
-    global_adv_kernel<<<1, 256, 0, st>>>(rewards, local_B, stat_rewards, n_stat, advantages);
+    launch_pdl(global_adv_kernel, 1, 256, 0, st, rewards, local_B, stat_rewards, n_stat, advantages);
     return (int)cudaGetLastError();
   }
   const int G = num_generations;
@@ -170,7 +173,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_group_advantages(c
   if (smem > 48 * 1024) return MIXGRPO_EINVAL;                                 // n_models * G <= ~12k rewards per group
   const int64_t n_groups = local_B / G;                                        // TR:444 (floor; tail untouched)
   if (n_groups <= 0) return 0;
-  group_adv_kernel<<<(unsigned)n_groups, kAdvThreads, smem, st>>>(rewards, weights, n_models, local_B, G, trim_size, advantages);
+  launch_pdl(group_adv_kernel, (unsigned)n_groups, kAdvThreads, smem, st, rewards, weights, n_models, local_B, G, trim_size, advantages);
   return (int)cudaGetLastError();
 }
 
@@ -180,7 +183,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_grpo_loss(const fl
   if (!new_logp || !old_logp || !advantages || !stats_out || B <= 0) return MIXGRPO_EINVAL;
   const LossParams q = make_loss_params(nullptr, nullptr, nullptr, clip_range, adv_clip_max, kl_coeff, denom);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (B <= 32) grpo_loss_kernel<32><<<1, 32, 0, st>>>(new_logp, old_logp, advantages, B, q, stats_out, grad_new_logp, stats_accum);
-  else grpo_loss_kernel<256><<<1, 256, 0, st>>>(new_logp, old_logp, advantages, B, q, stats_out, grad_new_logp, stats_accum);
+  if (B <= 32) launch_pdl(grpo_loss_kernel<32>, 1, 32, 0, st, new_logp, old_logp, advantages, B, q, stats_out, grad_new_logp, stats_accum);
+  else launch_pdl(grpo_loss_kernel<256>, 1, 256, 0, st, new_logp, old_logp, advantages, B, q, stats_out, grad_new_logp, stats_accum);
   return (int)cudaGetLastError();
 }

@@ -11,6 +11,7 @@ namespace mg {
 template <class T, bool PACK, bool AFFINE>
 __global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ src, T* __restrict__ dst, long long total_pairs,
                                                   int C, int H, int W, float divisor, float shift) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // one (dw=0,1) pair
   if (i >= total_pairs) return;
   const int Wp = W / 2, Hp = H / 2;
@@ -45,11 +46,11 @@ static int launch_pack(const void* src, void* dst, int dtype, int64_t B, int C, 
   const unsigned grid = (unsigned)((pairs + 255) / 256);
   const bool affine = !PACK && !(divisor == 1.f && shift == 0.f);
   if (dtype == MIXGRPO_F32) {
-    if (affine) pack_kernel<float, PACK, true><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
-    else pack_kernel<float, PACK, false><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
+    if (affine) launch_pdl(pack_kernel<float, PACK, true>, grid, 256, 0, st, (const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
+    else launch_pdl(pack_kernel<float, PACK, false>, grid, 256, 0, st, (const float*)src, (float*)dst, pairs, C, H, W, divisor, shift);
   } else if (dtype == MIXGRPO_BF16) {
-    if (affine) pack_kernel<__nv_bfloat16, PACK, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
-    else pack_kernel<__nv_bfloat16, PACK, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
+    if (affine) launch_pdl(pack_kernel<__nv_bfloat16, PACK, true>, grid, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
+    else launch_pdl(pack_kernel<__nv_bfloat16, PACK, false>, grid, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, pairs, C, H, W, divisor, shift);
   } else {
     return MIXGRPO_EINVAL;
   }
@@ -70,6 +71,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_unpack_latents(con
 namespace mg {
 template <class T, bool VECTOR>
 __global__ void __launch_bounds__(256) cast_rows_kernel(const T* __restrict__ src, float* __restrict__ dst, long long dst_bs, long long n) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * (VECTOR ? kVec : 1);
   if (i >= n) return;
@@ -92,11 +94,11 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_cast_rows(const vo
   const long long per = 256LL * (vec ? mg::kVec : 1);
   dim3 grid((unsigned)((n + per - 1) / per), (unsigned)B);
   if (src_dtype == MIXGRPO_BF16) {
-    if (vec) mg::cast_rows_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, dst_bs, n);
-    else mg::cast_rows_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, dst_bs, n);
+    if (vec) mg::launch_pdl(mg::cast_rows_kernel<__nv_bfloat16, true>, grid, 256, 0, st, (const __nv_bfloat16*)src, dst, dst_bs, n);
+    else mg::launch_pdl(mg::cast_rows_kernel<__nv_bfloat16, false>, grid, 256, 0, st, (const __nv_bfloat16*)src, dst, dst_bs, n);
   } else {
-    if (vec) mg::cast_rows_kernel<float, true><<<grid, 256, 0, st>>>((const float*)src, dst, dst_bs, n);
-    else mg::cast_rows_kernel<float, false><<<grid, 256, 0, st>>>((const float*)src, dst, dst_bs, n);
+    if (vec) mg::launch_pdl(mg::cast_rows_kernel<float, true>, grid, 256, 0, st, (const float*)src, dst, dst_bs, n);
+    else mg::launch_pdl(mg::cast_rows_kernel<float, false>, grid, 256, 0, st, (const float*)src, dst, dst_bs, n);
   }
   return (int)cudaGetLastError();
 }

@@ -198,6 +198,7 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
 __global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || WMEAN || !VECTOR || (FAM == kDance && SDE)) ? 4 : 6)
 step_kernel(const __grid_constant__ StepParams p) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const long long n = p.n;
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
@@ -288,6 +289,7 @@ step_kernel(const __grid_constant__ StepParams p) {
 
 // ------------------------------------------------------------------ host-side dispatch
 static int g_max_ctas_per_sample = kMaxCtasPerSample;   // bench knob (mixgrpo_set_tuning key 0)
+int g_use_pdl = 1;                                      // bench knob (key 1): programmatic dependent launch on/off
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -296,7 +298,7 @@ static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
   dim3 grid((unsigned)ctas, (unsigned)p.B);
-  step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, WMEAN><<<grid, kThreads, 0, st>>>(p);
+  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, WMEAN>, grid, kThreads, 0, st, p);
   return (int)cudaGetLastError();
 }
 
@@ -373,6 +375,12 @@ extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
+  if (key == 1) {
+    if (value != 0 && value != 1) return MIXGRPO_EINVAL;
+    const int old = g_use_pdl;
+    g_use_pdl = value;
+    return old;
+  }
   if (key != 0 || value < 1 || value > kMaxCtasPerSample) return MIXGRPO_EINVAL;
   const int old = g_max_ctas_per_sample;
   g_max_ctas_per_sample = value;

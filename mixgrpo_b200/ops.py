@@ -12,7 +12,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import BF16, F32, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, LossArgs, StepCoefs
+from ._cabi import BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, LossArgs, StepCoefs
 
 FLOW, DANCE, DPM = 0, 1, 2
 
@@ -236,8 +236,10 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
 
 def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, new_logp: torch.Tensor, coefs: StepCoefs,
                     old_logp: torch.Tensor, advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float,
-                    denom: float, round_like_torch: bool = False) -> torch.Tensor:
-    """Fused policy-update backward (mixgrpo_policy_bwd): d loss / d model_output, dtype = model_output.dtype."""
+                    denom: float, round_like_torch: bool = False, early_loads: bool = False) -> torch.Tensor:
+    """Fused policy-update backward (mixgrpo_policy_bwd): d loss / d model_output, dtype = model_output.dtype.
+    ``early_loads``: the caller launched ``policy_forward`` on the same inputs immediately before (nothing in between
+    writes v / x / x_next), so the kernel may load them while that launch drains (MIXGRPO_FLAG_PDL_EARLY_LOADS)."""
     global launch_count
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (new_logp, "new_log_probs")):
@@ -250,7 +252,7 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     nl = new_logp.detach().to(torch.float32).contiguous().view(-1)
     la, keep = _loss_args(old_logp, advantages, None, clip_range, adv_clip_max, kl_coeff, denom, B, dev)
     grad_v = torch.empty_like(v)
-    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early_loads else 0)
     with torch.cuda.device(dev):
         rc = lib.mixgrpo_policy_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, nl.data_ptr(), C.byref(la),
                                     grad_v.data_ptr(), B, n, C.byref(coefs), flags, _stream_ptr(dev))

@@ -196,6 +196,6 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     new_lp = _ops.policy_forward(fam, vd, latents, next_latents, k, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
                                  denom, stats_rows=stats_rows, round_like_torch=rnd)
     grad_v = _ops.policy_backward(fam, vd, latents, next_latents, new_lp, k, old_log_probs, advantages, clip_range, adv_clip_max,
-                                  kl_coeff, denom, round_like_torch=rnd)
+                                  kl_coeff, denom, round_like_torch=rnd, early_loads=True)   # launched right after the forward
     return stats_rows, new_lp, grad_v
 

@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_sde(const __grid_constant__ P p
   float* xo = p.xo + (long long)b * n;
   float* x0 = p.x0 + (long long)b * n;
   float acc = 0.f;
+  if constexpr (MATH >= 2) asm volatile("griddepcontrol.launch_dependents;");   // PDL: let the next grid start filling freed SMs
+  if constexpr (MATH == 2) asm volatile("griddepcontrol.wait;" ::: "memory");      // wait for the previous grid before ANY load
   if constexpr (VEC == 8) {
     uint4 v[UNROLL], e[UNROLL];
     float x[UNROLL][8];
@@ -134,7 +136,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_sde(const __grid_constant__ P p
     for (int u = 0; u < UNROLL; ++u) {
       idx[u] = (((long long)blockIdx.x * UNROLL + u) * WORK + threadIdx.x) * 8;
       if (!worker) idx[u] = n;
-      if (idx[u] < n) { v[u] = ld16<HINT>(vp + idx[u]); ld32<HINT>(xp + idx[u], x[u]); e[u] = ld16<HINT>(ep + idx[u]); }
+      if (idx[u] < n) { v[u] = ld16<HINT>(vp + idx[u]); e[u] = ld16<HINT>(ep + idx[u]); }
+    }
+    if constexpr (MATH == 3) asm volatile("griddepcontrol.wait;" ::: "memory");    // only x depends on the previous step
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (idx[u] < n) ld32<HINT>(xp + idx[u], x[u]);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -487,7 +494,17 @@ static void run(const char* name) {
   auto launch = [&](int i, cudaStream_t st) {
     P p{bufs[i].v, bufs[i].x, bufs[i].e, bufs[i].xo, bufs[i].x0, d_logp, d_partials, d_counters, d_packed, n, nblk, coef, coefb};
     if (REDUCE == 3) cudaMemsetAsync(d_logp, 0, B * sizeof(float), st);
-    kern<<<dim3(nblk, B), BLOCK, 0, st>>>(p);
+    if (MATH >= 2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nblk, B); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, kern, p));
+    } else {
+      kern<<<dim3(nblk, B), BLOCK, 0, st>>>(p);
+    }
     if (REDUCE == 2) k_finalize<<<B, 32, 0, st>>>(d_partials, nblk, n, coef, d_logp);
   };
   const float us = time_graph(launch, NS, REPS);
@@ -526,14 +543,9 @@ int main(int argc, char** argv) {
   }
   run<8, 1, H_NC_NA, 0, 256, 6>("v8 u1 noreduce");
   run<8, 1, H_NC_NA, 7, 256, 6>("v8 u1 packed atomic (current)");
-  run_tma<13, 512, 0>("tma ring13 512thr 1/SM", 148);
-  run_tma<6, 512, 0>("tma ring6 512thr 2/SM", 296);
-  run_tma<4, 512, 0>("tma ring4 512thr 3/SM", 444);
-  run_tma<6, 256, 0>("tma ring6 256thr 2/SM", 296);
-  run_tma<4, 256, 0>("tma ring4 256thr 3/SM", 444);
-  run_tma<3, 256, 0>("tma ring3 256thr 4/SM", 592);
-  run_tma<2, 256, 0>("tma ring2 256thr 6/SM", 888);
-  run_tma<6, 512, 1>("tma ring6 512thr 2/SM hmul2", 296);
-  run_tma<4, 512, 1>("tma ring4 512thr 3/SM hmul2", 444);
+  run<8, 1, H_NC_NA, 7, 256, 6, 2>("packed atomic + PDL wait-first");
+  run<8, 1, H_NC_NA, 7, 256, 6, 3>("packed atomic + PDL v,e before wait");
+  run<8, 1, H_NC_NA, 0, 256, 6, 2>("noreduce + PDL wait-first");
+  run<8, 1, H_NC_NA, 0, 256, 6, 3>("noreduce + PDL v,e before wait");
   return 0;
 }
