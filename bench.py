@@ -136,8 +136,8 @@ class Workload:
         self.eps = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(WINDOW)]
         self.rewards = torch.randn(N_MODELS, B, device=dev, generator=g)
         self.weights = torch.tensor([1.0, 0.5, 2.0], device=dev)
-        self.stats_rows = torch.zeros(B, 4, device=dev)     # per-sample (loss, policy, kl, clip_frac) accumulators
-        self.stats = torch.zeros(4, device=dev)
+        self.stats_rows = torch.zeros(WINDOW, B, 4, device=dev)   # per (window step, sample): loss, policy, kl, clip_frac
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(WINDOW)]
 
     def noises(self, window):
         nz = [None] * N_STEPS
@@ -146,7 +146,7 @@ class Workload:
         return nz
 
 
-def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=None, collectives=True):
+def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=None, collectives=True, parallel=True):
     """One GRPO iteration's hot path through the public API (mixgrpo_b200.rollout / .grpo)."""
     from mixgrpo_b200 import grpo, rollout as R
     v_list = v_list if v_list is not None else w.v
@@ -160,20 +160,26 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
         gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
         _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
     adv = grpo.compute_group_advantages(rew, B, w.weights)
-    w.stats_rows.zero_()
-    grads = []
-    for t in window:
-        _, _, gv = R.policy_update(v_list[t], traj[:, t], traj[:, t + 1], logps[:, t], adv, w.sig, t, w.cfg, clip_range=CLIP,
-                                   adv_clip_max=ADV_CLIP, kl_coeff=KL, gradient_accumulation_steps=GA,
-                                   num_train_timesteps=len(window), stats_rows=w.stats_rows)
-        grads.append(gv)
-    torch.sum(w.stats_rows, dim=0, out=w.stats)                         # what TR:588-600 accumulate, once per step
+    # the window's policy updates are independent of one another (TR:536-585 loops over them): one stream each, so
+    # their kernels overlap; every (step, sample) owns its stats row -> no zeroing, no race, summed when logged
+    cur = torch.cuda.current_stream(w.dev)
+    grads = [None] * len(window)
+    for j, t in enumerate(window):
+        s = w.side[j] if parallel else cur
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            _, _, grads[j] = R.policy_update(v_list[t], traj[:, t], traj[:, t + 1], logps[:, t], adv, w.sig, t, w.cfg, clip_range=CLIP,
+                                             adv_clip_max=ADV_CLIP, kl_coeff=KL, gradient_accumulation_steps=GA,
+                                             num_train_timesteps=len(window), stats_rows=w.stats_rows[j], accumulate=False)
+    if parallel:
+        for j in range(len(window)):
+            cur.wait_stream(w.side[j])
     if collectives:
-        grpo.reduce_step_stats(w.stats, group)
-    return w.stats, logps, grads
+        grpo.reduce_step_stats(w.stats_rows, group)
+    return w.stats_rows, logps, grads
 
 
-LAUNCHES_PER_STEP = 1 + N_STEPS + 1 + 2 * WINDOW  # our kernels: trajectory seed + 25 sampler + 1 advantage + 4 x (policy fwd, policy bwd)
+LAUNCHES_PER_STEP = 1 + N_STEPS + 1 + 2 * WINDOW  # all ours: trajectory seed + 25 sampler + 1 advantage + 4 x (policy fwd, policy bwd)
 
 
 def capture_step(w: Workload, window):
@@ -312,7 +318,7 @@ def e2e_run(w: Workload, window, steps: int, warmup: int):
                 return dv[i]
         main.wait_event(evs[0])
         stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=de, rewards=dr)
-        h_stats.copy_(stats, non_blocking=True)
+        h_stats.copy_(stats.sum(dim=(0, 1)), non_blocking=True)
         h_lp.copy_(logps, non_blocking=True)
         main.synchronize()
         return float(h_stats[0])
@@ -378,7 +384,7 @@ def run_native(args):
             comm_stream.wait_stream(main_stream)
             with torch.cuda.stream(comm_stream):
                 grpo.gather_rewards(w.rewards)
-                grpo.reduce_step_stats(w.stats)
+                grpo.reduce_step_stats(w.stats_rows)
 
     for _ in range(args.warmup):
         step()
@@ -412,7 +418,7 @@ def run_native(args):
     ms_per_step = max_over_ranks(ms / args.steps, dev)
     total_bytes = algorithmic_bytes_per_step() * world
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
-    loss_host = float(stats[0].item())
+    loss_host = float(stats.sum(dim=(0, 1))[0].item())
 
     e2e_s, h2d, d2h, e2e_loss = e2e_run(w, window, max(2, min(args.steps, 5)), 2)
     e2e_s = max_over_ranks(e2e_s, dev)

@@ -157,8 +157,9 @@ int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, 
 typedef struct mixgrpo_loss_args {
   const float* old_logp;     /* [B] device */
   const float* advantages;   /* [B] device (unclamped; adv_clip_max is applied inside, TR:560-564) */
-  float* stats_rows;         /* [B,4] device, accumulated; may be NULL */
+  float* stats_rows;         /* [B,4] device; may be NULL */
   double clip_range, adv_clip_max, kl_coeff, denom;
+  int accumulate;            /* 1: stats_rows[b] += terms (running sum over window steps); 0: stats_rows[b] = terms */
 } mixgrpo_loss_args;
 
 int mixgrpo_policy_fwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,

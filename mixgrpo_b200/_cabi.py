@@ -26,7 +26,8 @@ class StepCoefs(C.Structure):
 class LossArgs(C.Structure):
     """mirror of ``mixgrpo_loss_args`` (include/mixgrpo_b200.h)."""
     _fields_ = [("old_logp", C.c_void_p), ("advantages", C.c_void_p), ("stats_rows", C.c_void_p),
-                ("clip_range", C.c_double), ("adv_clip_max", C.c_double), ("kl_coeff", C.c_double), ("denom", C.c_double)]
+                ("clip_range", C.c_double), ("adv_clip_max", C.c_double), ("kl_coeff", C.c_double), ("denom", C.c_double),
+                ("accumulate", C.c_int)]
 
 
 _P, _I64, _I, _U, _F, _D = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float, C.c_double

@@ -129,7 +129,7 @@ static int logprob_bwd_impl(int family, const void* v, int v_dtype, const float*
   BwdParams p;
   p.v = v; p.x = x; p.x_next = x_next; p.grad_logp = grad_logp; p.grad_v = grad_v;
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.k = *coefs_host;
-  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
   if (loss) p.loss = make_loss_params(loss->old_logp, loss->advantages, nullptr, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
   auto al = [](const void* q, size_t a) { return (reinterpret_cast<uintptr_t>(q) % a) == 0; };
   const size_t va = v_dtype == MIXGRPO_BF16 ? 16 : 32;

@@ -143,6 +143,7 @@ struct LossParams {
   const float* adv;        // [B]
   float* rows;             // [B,4] running (loss, policy, kl, clip_frac) per sample, or nullptr
   float clip, lo, hi, amax, klc, denom;
+  int accumulate;          // rows[b] += terms (1) or rows[b] = terms (0)
 };
 
 struct LossTerms {
@@ -159,6 +160,7 @@ __host__ inline LossParams make_loss_params(const float* old_lp, const float* ad
   // python scalars are narrowed to fp32 exactly where torch narrows them; 1 -/+ clip is formed in double (TR:571-572)
   q.clip = (float)clip_range; q.lo = (float)(1.0 - clip_range); q.hi = (float)(1.0 + clip_range);
   q.amax = (float)adv_clip_max; q.klc = (float)kl_coeff; q.denom = (float)denom;
+  q.accumulate = 1;
   return q;
 }
 

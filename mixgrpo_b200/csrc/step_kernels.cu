@@ -277,10 +277,9 @@ step_kernel(const __grid_constant__ StepParams p) {
           const float policy = __fdiv_rn(t.policy_num, p.loss.denom);
           const float kl = __fdiv_rn(__fmul_rn(0.5f, t.kl_num), p.loss.denom);
           float* row = p.loss.rows + 4 * (long long)b;
-          row[0] += __fadd_rn(policy, __fmul_rn(p.loss.klc, kl));
-          row[1] += policy;
-          row[2] += kl;
-          row[3] += t.clip;
+          const float4 prev = p.loss.accumulate ? *reinterpret_cast<const float4*>(row) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(row) = make_float4(prev.x + __fadd_rn(policy, __fmul_rn(p.loss.klc, kl)), prev.y + policy,
+                                                        prev.z + kl, prev.w + t.clip);
         }
       }
     }
@@ -353,7 +352,7 @@ static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, con
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
   p.B = (int)B; p.tiles = 0; p.k = *k;
-  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
+  p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
 }
 
 // 256-bit path needs 32-B aligned fp32 streams, 16-B aligned bf16 streams and n, strides % 8 == 0.
@@ -470,7 +469,11 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int fam
   if (loss && (!loss->old_logp || !loss->advantages)) return MIXGRPO_EINVAL;
   StepParams p;
   fill(p, v, x, x_bs, nullptr, x_next, in_bs, nullptr, nullptr, nullptr, n, nullptr, nullptr, logp_out, workspace, B, n, coefs_host);
-  if (loss) p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
+  if (loss) {
+    if (loss->stats_rows && (reinterpret_cast<uintptr_t>(loss->stats_rows) % 16) != 0) return MIXGRPO_EINVAL;   // rows are float4
+    p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
+    p.loss.accumulate = loss->accumulate ? 1 : 0;
+  }
   const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;

@@ -187,7 +187,7 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
     return grad_v
 
 
-def _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, device):
+def _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, device, accumulate=True):
     keep = []
     def vec(t, name):
         _require_cuda(t, name)
@@ -204,13 +204,14 @@ def _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_co
             raise ValueError("mixgrpo_b200: stats_rows must be a contiguous fp32 [B, 4] tensor on the same device")
         la.stats_rows = stats_rows.data_ptr()
     la.clip_range, la.adv_clip_max, la.kl_coeff, la.denom = float(clip_range), float(adv_clip_max), float(kl_coeff), float(denom)
+    la.accumulate = 1 if accumulate else 0
     return la, keep
 
 
 def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, coefs: StepCoefs, old_logp: torch.Tensor,
                    advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float, denom: float,
                    stats_rows: Optional[torch.Tensor] = None, round_like_torch: bool = False,
-                   out_logp: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out_logp: Optional[torch.Tensor] = None, accumulate: bool = True) -> torch.Tensor:
     """Fused policy-update forward (mixgrpo_policy_fwd): new log-probs [B]; per-sample loss terms += stats_rows."""
     global launch_count
     lib = _cabi.lib()
@@ -221,7 +222,7 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
     B, n, dev = v.shape[0], v[0].numel(), v.device
     x, x_bs = _rows(x.to(torch.float32), "latents")
     x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
-    la, keep = _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, dev)
+    la, keep = _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, dev, accumulate)
     logp = out_logp if out_logp is not None else torch.empty((B,), dtype=torch.float32, device=dev)
     ws = _workspace(dev, B, n)
     flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0

@@ -176,11 +176,12 @@ def balance_pos_neg(samples: List[dict], use_random: bool = False, rng: Optional
 def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Tensor, old_log_probs: torch.Tensor,
                   advantages: torch.Tensor, sigmas: torch.Tensor, index: int, cfg: SamplerConfig, *, clip_range: float,
                   adv_clip_max: float, kl_coeff: float, gradient_accumulation_steps: int, num_train_timesteps: int,
-                  stats_rows: Optional[torch.Tensor] = None):
+                  stats_rows: Optional[torch.Tensor] = None, accumulate: bool = True):
     """One (samples, window step) policy update, TR:542-585 without autograd: given the model output ``v`` for
     the stored ``latents`` it returns ``(stats_rows, new_log_probs [B], grad_v)`` where ``grad_v`` is dloss/dv — hand it
     to ``v.backward(grad_v)`` to continue into the DiT.  ``stats_rows`` ([B,4] fp32, optional) accumulates each sample's
-    (loss, policy_loss, kl_loss, clip_frac); ``stats_rows.sum(0)`` is what TR:588-600 adds up.  Two launches, no sync."""
+    (loss, policy_loss, kl_loss, clip_frac) (``accumulate=False`` overwrites instead); ``stats_rows.sum(0)`` is what
+    TR:588-600 adds up.  Two launches, no sync."""
     mode = _mode(cfg.rounding)
     bf16_v = v.dtype == torch.bfloat16
     rnd = bf16_v and mode != "fp32"
@@ -194,7 +195,7 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     # sample's stats row, backward = dL/dlogp evaluated in place + closed-form chain.  Two launches, no loss kernel.
     denom = float(gradient_accumulation_steps * num_train_timesteps)
     new_lp = _ops.policy_forward(fam, vd, latents, next_latents, k, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
-                                 denom, stats_rows=stats_rows, round_like_torch=rnd)
+                                 denom, stats_rows=stats_rows, round_like_torch=rnd, accumulate=accumulate)
     grad_v = _ops.policy_backward(fam, vd, latents, next_latents, new_lp, k, old_log_probs, advantages, clip_range, adv_clip_max,
                                   kl_coeff, denom, round_like_torch=rnd, early_loads=True)   # launched right after the forward
     return stats_rows, new_lp, grad_v

@@ -361,3 +361,58 @@ def test_cast_rows_seeds_trajectory_slot():
         ops.cast_rows(z.to(d), traj[:, 0])
         assert torch.equal(traj[:, 0].cpu(), z.float())
         assert torch.equal(traj[:, 1:].cpu(), torch.full((shape[0], 2) + shape[1:], -1.0))
+
+
+def test_no_out_of_bounds_writes_canaries():
+    """compute-sanitizer is closed on this pool, so writes are fenced by hand: every output lives inside a larger buffer
+    filled with a sentinel; after the kernels run on vector-sized, ragged and tiny shapes the guard bands must be intact."""
+    from mixgrpo_b200 import coefs, ops
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+    d = _dev()
+    SENT, PAD = -12345.0, 4096
+    g = torch.Generator().manual_seed(4)
+
+    def guarded(shape, dtype=torch.float32):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        buf = torch.full((n + 2 * PAD,), SENT, dtype=dtype, device=d)
+        return buf, buf[PAD:PAD + n].view(shape)
+
+    def intact(buf, n):
+        return bool((buf[:PAD] == SENT).all() and (buf[PAD + n:] == SENT).all())
+
+    for shape in [(3, 64, 64), (2, 2049), (5, 7, 3), (1, 1, 1), (4, 2048), (2, 4104)]:
+        n = 1
+        for s_ in shape:
+            n *= s_
+        x = torch.randn(*shape, generator=g).to(d)
+        v = torch.randn(*shape, generator=g).bfloat16().to(d)
+        e = torch.randn(*shape, generator=g).bfloat16().to(d)
+        k, _ = coefs.flow(SIG, 5, ETA, "ref_cuda", True)
+        for src in (SRC_NOISE, SRC_DETERMINISTIC):
+            ob, out = guarded(shape)
+            lb, lp = guarded((shape[0],))
+            xn, x0, _, mean = ops.fused_step(ops.FLOW, v, x, k, src=src, noise=e if src == SRC_NOISE else None, out_x_next=out,
+                                             out_logp=lp, want_x0=True, want_mean=True, round_like_torch=True)
+            torch.cuda.synchronize()
+            assert intact(ob, n) and intact(lb, shape[0]), (shape, src)
+            assert torch.isfinite(out).all() and torch.isfinite(lp).all()
+        # backward + cast into guarded buffers
+        lp = ops.fused_step(ops.FLOW, v, x, k, src=SRC_GIVEN, x_next=out, want_x0=False, round_like_torch=True)[2]
+        gv = ops.logprob_backward(ops.FLOW, v, x, out, torch.ones_like(lp), k, True)
+        assert gv.shape == v.shape and torch.isfinite(gv.float()).all()
+        cb, cdst = guarded(shape)
+        ops.cast_rows(v, cdst)
+        torch.cuda.synchronize()
+        assert intact(cb, n) and torch.equal(cdst, v.float())
+    # ordered dpm history streams on a ragged shape
+    shape = (2, 1027)
+    x = torch.randn(*shape, generator=g).to(d)
+    v = torch.randn(*shape, generator=g).to(d)
+    m1, m2 = torch.randn(*shape, generator=g).to(d), torch.randn(*shape, generator=g).to(d)
+    k, _ = coefs.dpm(SIG, 6, 3, "dpmsolver++", "midpoint", "fp32", False)
+    ob, out = guarded(shape)
+    ops.fused_step(ops.DPM, v, x, k, src=SRC_DETERMINISTIC, m1=m1, m2=m2, order=3, out_x_next=out)
+    torch.cuda.synchronize()
+    assert intact(ob, 2 * 1027)
