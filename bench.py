@@ -19,8 +19,8 @@ metric  = sampler-step latent GB/s = algorithmic bytes of all sampler/log-prob k
 roofline= the fused SDE step + log-prob kernel with the reference's full output signature
           (prev_sample, pred_x0, log_prob: 16 B/elem), timed by CUDA events over graph replays on
           rotating buffer sets larger than L2.
-e2e     = the same step through the public Python API with HOST (pinned) model outputs/noise/rewards,
-          H2D + D2H copies inside the timed region.
+e2e     = the same step through the public Python API with HOST (pinned) model outputs and rewards, H2D + D2H copies
+          inside the timed region (the SDE noise is drawn on the device, as the reference does).
 --impl reference: the reference's algorithm on the host cores (oracle/: torch-CPU restatement pinned
           bit-exact to the reference — the reference itself is pure PyTorch, so this IS its CPU path).
 """
@@ -281,22 +281,22 @@ def measure_roofline(dev, peak_gbs, peak_kind):
 
 
 def e2e_run(w: Workload, window, steps: int, warmup: int):
-    """Same step with HOST inputs: every step copies its 25 model outputs, 4 noise tensors and the rewards from pinned
-    host memory, runs through the public API (eager launches), and reads stats + log-probs back."""
+    """Same step with HOST inputs: every step copies its 25 model outputs and the rewards from pinned host memory, runs
+    through the public API (eager launches), and reads the stats rows + log-probs back.  The SDE noise is drawn on the
+    device, as in the reference (randn_tensor(..., device=model_output.device), SU:189-194) — it is not an input."""
     hv = [torch.empty(B, S, C, dtype=torch.bfloat16).pin_memory() for _ in range(N_STEPS)]
-    he = [torch.empty(B, S, C, dtype=torch.bfloat16).pin_memory() for _ in range(WINDOW)]
     hr = torch.randn(N_MODELS, B).pin_memory()
-    for t in hv + he:
+    for t in hv:
         t.normal_()
     dv = [torch.empty_like(t, device=w.dev) for t in hv]
-    de = [torch.empty_like(t, device=w.dev) for t in he]
     dr = torch.empty(N_MODELS, B, device=w.dev)
-    h_stats = torch.empty(4).pin_memory()
+    h_stats = torch.empty(WINDOW, B, 4).pin_memory()
     h_lp = torch.empty(B, N_STEPS).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in hv + he) + hr.numel() * 4
+    h2d = sum(t.numel() * t.element_size() for t in hv) + hr.numel() * 4
     d2h = h_stats.numel() * 4 + h_lp.numel() * 4
     copy_stream = torch.cuda.Stream(device=w.dev)
     main = torch.cuda.current_stream(w.dev)
+    gen = torch.Generator(device=w.dev).manual_seed(99)
 
     def one():
         # H2D on a copy stream, one event per tensor, so step i's kernel only waits for ITS model output
@@ -304,8 +304,6 @@ def e2e_run(w: Workload, window, steps: int, warmup: int):
         copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
             dr.copy_(hr, non_blocking=True)
-            for j in range(WINDOW):
-                de[j].copy_(he[j], non_blocking=True)
             for i in range(N_STEPS):
                 dv[i].copy_(hv[i], non_blocking=True)
                 ev = torch.cuda.Event()
@@ -317,11 +315,12 @@ def e2e_run(w: Workload, window, steps: int, warmup: int):
                 main.wait_event(evs[i])
                 return dv[i]
         main.wait_event(evs[0])
-        stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=de, rewards=dr)
-        h_stats.copy_(stats.sum(dim=(0, 1)), non_blocking=True)
+        eps = [torch.randn(B, S, C, device=w.dev, dtype=torch.bfloat16, generator=gen) for _ in range(WINDOW)]
+        stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=eps, rewards=dr)
+        h_stats.copy_(stats, non_blocking=True)
         h_lp.copy_(logps, non_blocking=True)
         main.synchronize()
-        return float(h_stats[0])
+        return float(h_stats.sum(dim=(0, 1))[0])
 
     for _ in range(warmup):
         one()
@@ -420,7 +419,7 @@ def run_native(args):
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
     loss_host = float(stats.sum(dim=(0, 1))[0].item())
 
-    e2e_s, h2d, d2h, e2e_loss = e2e_run(w, window, max(2, min(args.steps, 5)), 2)
+    e2e_s, h2d, d2h, e2e_loss = e2e_run(w, window, max(3, min(args.steps, 20)), 3)
     e2e_s = max_over_ranks(e2e_s, dev)
     e2e_value = total_bytes / e2e_s / 1e9
 

@@ -302,7 +302,9 @@ def group_advantages(rewards: torch.Tensor, weights: Optional[torch.Tensor], num
     if stat_rewards is not None:
         stat_rewards = stat_rewards.to(device=r.device, dtype=torch.float32).contiguous()
         s_p, n_stat = stat_rewards.data_ptr(), stat_rewards.numel()
-    adv = torch.zeros((local_B,), dtype=torch.float32, device=r.device)
+    # every entry is written unless a ragged tail (local_B % G) exists, which the reference leaves at zero (TR:445)
+    full = (not use_group) or (local_B % int(num_generations) == 0)
+    adv = (torch.empty if full else torch.zeros)((local_B,), dtype=torch.float32, device=r.device)
     with torch.cuda.device(r.device):
         rc = lib.mixgrpo_group_advantages(r.data_ptr(), w_p, n_models, local_B, int(num_generations), int(trim_size),
                                           1 if use_group else 0, s_p, n_stat, adv.data_ptr(), _stream_ptr(r.device))
