@@ -416,3 +416,41 @@ def test_no_out_of_bounds_writes_canaries():
     ops.fused_step(ops.DPM, v, x, k, src=SRC_DETERMINISTIC, m1=m1, m2=m2, order=3, out_x_next=out)
     torch.cuda.synchronize()
     assert intact(ob, 2 * 1027)
+
+
+@pytest.mark.parametrize("B,S", [(12, 4096), (24, 1024), (24, 4096)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_full_size_bit_exact_vs_reference_ops_on_device(B, S, dtype):
+    """BASELINE configs[1]/[4] at FULL size: group 12 / 24, 512^2-1024^2 latents.  The checker is the reference's own op
+    sequence executed on the same B200 (oracle functions on CUDA tensors; pinned bit-exact to the reference on CUDA by
+    tests/golden/probe_cuda_rounding_b200.json).  Default rounding: prev / x0 bit-exact, log-prob 1e-5, bf16 gradient
+    bit-exact; plus the fp32-vs-bf16 log-prob tolerance check of configs[4]."""
+    from mixgrpo_b200 import sampling_utils as su
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(B * S)
+    x = torch.randn(B, S, 64, device=d, generator=g)
+    v32 = torch.randn(B, S, 64, device=d, generator=g)
+    v = v32.to(dtype)
+    eps = torch.randn(B, S, 64, device=d, generator=g).to(dtype)
+    sig = SIG.to(d)
+    for idx, det in ((0, False), (9, False), (24, False), (5, True)):
+        out = su.flow_grpo_step(v, x, ETA, sig, idx, None, determistic=det, noise=eps, return_mean=False)
+        ref = O.flow_step(v, x, ETA, sig, idx, None, eps, det)
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]), (idx, det)
+        assert torch.allclose(out[2], ref[2], rtol=1e-5, atol=0)
+    idx = 9
+    xn = ref_xn = O.flow_step(v, x, ETA, sig, idx, None, eps, False)[0]
+    vg = v.clone().requires_grad_(True)
+    lp = su.flow_grpo_step(vg, x, ETA, sig, idx, xn)[2]
+    vr = v.clone().requires_grad_(True)
+    rlp = O.flow_step(vr, x, ETA, sig, idx, ref_xn)[2]
+    w = torch.linspace(-1, 1, B, device=d)
+    (lp * w).sum().backward()
+    (rlp * w).sum().backward()
+    assert torch.allclose(lp, rlp, rtol=1e-5, atol=0)
+    assert torch.equal(vg.grad, vr.grad)
+    if dtype == torch.float32:
+        # configs[4]: the same transition scored with the model output rounded to bf16 (what autocast hands over)
+        lp16 = su.flow_grpo_step(v32.bfloat16(), x, ETA, sig, idx, xn)[2]
+        rel = ((lp16 - lp.detach()).abs() / lp.detach().abs()).max().item()
+        assert rel < 5e-3, rel          # bf16 quantisation of v moves the mean by <= 2^-9 relative: log-prob within 0.5 %
