@@ -46,7 +46,7 @@ B, S, C = 12, 4096, 64          # group size, packed tokens (1024^2), channels
 N_STEPS, WINDOW, N_MODELS = 25, 4, 3
 ETA, SHIFT = 0.7, 3.0
 CLIP, ADV_CLIP, KL, GA = 1e-4, 5.0, 0.01, 3
-BYTES = {"ode": 10, "sde": 12, "sde_x0": 16, "train_fwd": 10, "bwd": 12}   # SURVEY §8d, bf16 v/noise
+BYTES = {"ode": 10, "sde": 12, "sde_x0": 16, "train_fwd": 10, "bwd": 12, "sde_x0_philox": 14}   # SURVEY §8d, bf16 v/noise
 
 
 def algorithmic_bytes_per_step() -> int:
@@ -201,7 +201,7 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     """CUDA-event time per launch of the fused SDE step + log-prob kernel (16 B/elem signature) and its siblings,
     replayed from a CUDA graph over 10 rotating buffer sets (10 x 50 MB > 126 MB L2)."""
     from mixgrpo_b200 import coefs, ops
-    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX
     ns = 10
     g = torch.Generator(device=dev).manual_seed(7)
     xs = [torch.randn(B, S, C, device=dev, generator=g) for _ in range(ns)]
@@ -226,10 +226,12 @@ def measure_roofline(dev, peak_gbs, peak_kind):
             ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_GIVEN, x_next=outs[(i + 1) % ns], out_logp=lps[i], want_x0=False, round_like_torch=True)
         elif kind == "bwd":
             ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True)
+        elif kind == "sde_x0_philox":      # noise drawn in the kernel: no noise tensor is read (and none was generated)
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_PHILOX, philox=(1234, 4 * i), out_x_next=outs[i], out_logp=lps[i], want_x0=True, round_like_torch=True)
 
     res = {}
     s = torch.cuda.Stream(device=dev)
-    for kind in ("sde_x0", "sde", "ode", "train_fwd", "bwd"):
+    for kind in ("sde_x0", "sde", "ode", "train_fwd", "bwd", "sde_x0_philox"):
         with torch.cuda.stream(s):
             for i in range(ns):
                 run(kind, i)

@@ -36,8 +36,20 @@ enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
 enum {
   MIXGRPO_SRC_NOISE = 0,        /* rollout, SDE:  x_next = mean + scale*noise   (SU:188-195, SU:238, SU:434) */
   MIXGRPO_SRC_GIVEN = 1,        /* policy update: x_next supplied (prev_sample=, TR:149-157)               */
-  MIXGRPO_SRC_DETERMINISTIC = 2 /* rollout, ODE:  Euler / DPM closed form       (SU:198-199, SU:240, SU:436) */
+  MIXGRPO_SRC_DETERMINISTIC = 2,/* rollout, ODE:  Euler / DPM closed form       (SU:198-199, SU:240, SU:436) */
+  MIXGRPO_SRC_PHILOX = 3        /* rollout, SDE with the noise drawn IN the kernel (replaces the randn_tensor /
+                                   randn_like launch and its 2-4 B/elem read, SU:189-194, SU:238, SU:319-321):
+                                   `noise` is then a HOST pointer to a mixgrpo_philox_args                     */
 };
+
+/* Counter-based noise for MIXGRPO_SRC_PHILOX: element e = b*n + i of the (B, n) tensor gets component (e mod 4) of
+ * Philox4x32-10(counter = {e/4 (64 bit), offset (64 bit)}, key = seed ^ tag) through Box-Muller, i.e. a pure function
+ * of (seed, offset, e) — independent of the launch configuration, reproducible, and reproducible on the host
+ * (oracle/philox_oracle.py).  Rounded to bf16 when the family's noise dtype is bf16 (flow with bf16 model output). */
+typedef struct mixgrpo_philox_args {
+  uint64_t seed;
+  uint64_t offset;
+} mixgrpo_philox_args;
 
 /* flags */
 #define MIXGRPO_FLAG_ROUND_LIKE_TORCH 1u /* reproduce torch's bf16 type-promotion roundings */

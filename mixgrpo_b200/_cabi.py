@@ -12,7 +12,7 @@ from typing import Optional
 from . import _build
 
 F32, BF16 = 0, 1
-SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC = 0, 1, 2
+SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC, SRC_PHILOX = 0, 1, 2, 3
 FLAG_ROUND_LIKE_TORCH = 1
 FLAG_PDL_EARLY_LOADS = 2
 ABI_VERSION = 1
@@ -21,6 +21,11 @@ ABI_VERSION = 1
 class StepCoefs(C.Structure):
     """mirror of ``mixgrpo_step_coefs`` (include/mixgrpo_b200.h)."""
     _fields_ = [("two_var", C.c_float), ("log_scale", C.c_float), ("log_norm", C.c_float), ("c", C.c_float * 16)]
+
+
+class PhiloxArgs(C.Structure):
+    """mirror of ``mixgrpo_philox_args`` (include/mixgrpo_b200.h)."""
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64)]
 
 
 class LossArgs(C.Structure):

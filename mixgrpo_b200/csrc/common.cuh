@@ -85,6 +85,33 @@ __device__ __forceinline__ void round_like_torch(float (&r)[N]) {
   }
 }
 
+// ---------------------------------------------------------------- in-kernel normal noise (MIXGRPO_SRC_PHILOX)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// four N(0,1) samples for elements 4q .. 4q+3 (q = element index / 4)
+__device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned long long seed, unsigned long long offset, float (&z)[4]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x6d697867u));
+  // 24-bit uniforms in (0,1): never 0, so the log is finite
+  const float u0 = ((float)(r.x >> 8) + 0.5f) * 5.9604644775390625e-08f, u1 = ((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  const float u2 = ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-08f, u3 = ((float)(r.w >> 8) + 0.5f) * 5.9604644775390625e-08f;
+  const float ra = sqrtf(-2.f * __logf(u0)), rb = sqrtf(-2.f * __logf(u2));
+  float sa, ca, sb, cb;
+  __sincosf(6.283185307179586f * u1, &sa, &ca);
+  __sincosf(6.283185307179586f * u3, &sb, &cb);
+  z[0] = ra * ca; z[1] = ra * sa; z[2] = rb * cb; z[3] = rb * sb;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
 //   griddepcontrol.wait              -> the previous grid on the stream has completed and its writes are visible

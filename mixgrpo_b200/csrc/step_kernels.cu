@@ -37,6 +37,7 @@ struct StepParams {
   long long n, x_bs, in_bs, out_bs;
   int B, tiles;
   mixgrpo_step_coefs k;
+  unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
   LossParams loss;          // fused policy path (SRC_GIVEN only): old log-probs / advantages / stats rows, or nullptrs
 };
 
@@ -196,7 +197,7 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
-__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || WMEAN || !VECTOR || (FAM == kDance && SDE)) ? 4 : 6)
+__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || WMEAN || !VECTOR || (FAM == kDance && SDE)) ? 4 : (SRC == MIXGRPO_SRC_PHILOX ? 5 : 6))
 step_kernel(const __grid_constant__ StepParams p) {
   pdl_prologue();
   const int b = blockIdx.y;
@@ -213,6 +214,25 @@ step_kernel(const __grid_constant__ StepParams p) {
     load_tile<VT, VECTOR>(vp, off, n, v);
     load_tile<float, VECTOR>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
+    if constexpr (SRC == MIXGRPO_SRC_PHILOX) {     // draw the noise here: element e -> component e%4 of Philox(e/4)
+      if constexpr (VECTOR) {
+        const unsigned long long e0 = (unsigned long long)b * n + off + threadIdx.x * kVec;
+        float z0[4], z1[4];
+        philox_normal4(e0 >> 2, p.philox_seed, p.philox_offset, z0);
+        philox_normal4((e0 >> 2) + 1, p.philox_seed, p.philox_offset, z1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[j] = z0[j]; a[4 + j] = z1[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+          const unsigned long long e = (unsigned long long)b * n + off + j * kThreads + threadIdx.x;
+          float z[4];
+          philox_normal4(e >> 2, p.philox_seed, p.philox_offset, z);
+          a[j] = z[e & 3];
+        }
+      }
+      if constexpr (sizeof(NT) == 2) round_like_torch<true>(a);        // the noise tensor itself is bf16 (SU:193)
+    }
     if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR>(p.x_in + (long long)b * p.in_bs, off, n, a);
     if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
     if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
@@ -223,7 +243,7 @@ step_kernel(const __grid_constant__ StepParams p) {
       const float v2[2] = {v[j], v[j + 1]}, x2[2] = {x[j], x[j + 1]}, a2[2] = {a[j], a[j + 1]};
       const float m12[2] = {m1[j], m1[j + 1]}, m22[2] = {m2[j], m2[j + 1]};
       float xn2[2], x02[2], mu2[2], dd2[2];
-      tile_math<FAM, SRC, ORDER, RND, SDE>(p.k, v2, x2, a2, m12, m22, xn2, x02, mu2, dd2);
+      tile_math<FAM, (SRC == MIXGRPO_SRC_PHILOX ? MIXGRPO_SRC_NOISE : SRC), ORDER, RND, SDE>(p.k, v2, x2, a2, m12, m22, xn2, x02, mu2, dd2);
       xn[j] = xn2[0]; xn[j + 1] = xn2[1];
       x0[j] = x02[0]; x0[j + 1] = x02[1];
       if constexpr (WMEAN) { mu[j] = mu2[0]; mu[j + 1] = mu2[1]; }
@@ -325,6 +345,7 @@ static int pick_src(StepParams& p, int64_t B, int src, bool vec_ok, cudaStream_t
       if constexpr (FAM == kDpm) return MIXGRPO_EINVAL;   // dpm_step has no prev_sample argument (SU:273-284)
       else return pick_width<FAM, VT, NT, MIXGRPO_SRC_GIVEN, ORDER, RND, SDE>(p, B, vec_ok, st);
     case MIXGRPO_SRC_DETERMINISTIC: return pick_width<FAM, VT, NT, MIXGRPO_SRC_DETERMINISTIC, ORDER, RND, SDE>(p, B, vec_ok, st);
+    case MIXGRPO_SRC_PHILOX: return pick_width<FAM, VT, NT, MIXGRPO_SRC_PHILOX, ORDER, RND, SDE>(p, B, vec_ok, st);
   }
   return MIXGRPO_EINVAL;
 }
@@ -352,6 +373,7 @@ static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, con
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
   p.B = (int)B; p.tiles = 0; p.k = *k;
+  p.philox_seed = p.philox_offset = 0ull;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
 }
 
@@ -393,9 +415,10 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_flow_step(const vo
                                  int src, unsigned flags, void* stream) {
   int err = 0;
   if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
-  if ((src == MIXGRPO_SRC_NOISE && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
+  if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
   StepParams p;
-  fill(p, v, x, x_bs, noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = static_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
   const bool vec = vector_ok(p, v_dtype, v_dtype, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
@@ -410,9 +433,10 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_dance_step(const v
                                   int src, int sde_solver, unsigned flags, void* stream) {
   int err = 0;
   if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
-  if ((src == MIXGRPO_SRC_NOISE && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
+  if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
   StepParams p;
-  fill(p, v, x, x_bs, noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = reinterpret_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
   const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
@@ -443,9 +467,10 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_dpm_step(const voi
   int err = 0;
   if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
   if (order < 1 || order > 3 || (order >= 2 && !m1) || (order == 3 && !m2)) return MIXGRPO_EINVAL;
-  if (src == MIXGRPO_SRC_NOISE && !noise) return MIXGRPO_EINVAL;
+  if ((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) return MIXGRPO_EINVAL;
   StepParams p;
-  fill(p, v, x, x_bs, noise, nullptr, n, m1, m2, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, nullptr, n, m1, m2, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = reinterpret_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
   const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;

@@ -12,7 +12,8 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, LossArgs, StepCoefs
+from ._cabi import (BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX,
+                    LossArgs, PhiloxArgs, StepCoefs)
 
 FLOW, DANCE, DPM = 0, 1, 2
 
@@ -65,12 +66,27 @@ def _workspace(device: torch.device, B: int, n: int) -> torch.Tensor:
     return ws
 
 
+def philox_from_generator(device: torch.device, numel: int, generator: Optional[torch.Generator] = None) -> Tuple[int, int]:
+    """(seed, offset) for MIXGRPO_SRC_PHILOX taken from a torch CUDA generator (the device default when None), whose
+    Philox offset is advanced past the ``numel`` normals consumed — later torch.randn calls draw fresh numbers, and
+    ``torch.manual_seed`` / ``generator.manual_seed`` reproduce the in-kernel noise too."""
+    if generator is None or generator.device.type != "cuda":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        seed_src = generator
+        generator = torch.cuda.default_generators[idx]
+        if seed_src is not None:                       # a CPU generator only lends its seed
+            return int(seed_src.initial_seed()), int(torch.randint(0, 2 ** 31, (1,), generator=seed_src).item()) * 4
+    seed, off = int(generator.initial_seed()), int(generator.get_offset())
+    generator.set_offset(off + 4 * ((numel + 3) // 4))
+    return seed, off
+
+
 def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, *, src: int,
                noise: Optional[torch.Tensor] = None, x_next: Optional[torch.Tensor] = None,
                m1: Optional[torch.Tensor] = None, m2: Optional[torch.Tensor] = None, order: int = 1,
                sde_solver: bool = True, out_x_next: Optional[torch.Tensor] = None, want_x0: bool = True,
                want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
-               out_logp: Optional[torch.Tensor] = None):
+               out_logp: Optional[torch.Tensor] = None, philox: Optional[Tuple[int, int]] = None):
     """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
     requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in."""
     global launch_count
@@ -101,6 +117,12 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
             raise ValueError("mixgrpo_b200: noise shape mismatch")
         noise_p = noise.data_ptr()
         keep.append(noise)
+    elif src == SRC_PHILOX:
+        if philox is None:
+            raise ValueError("mixgrpo_b200: in-kernel noise needs philox=(seed, offset)")
+        pa = PhiloxArgs(int(philox[0]) & 0xFFFFFFFFFFFFFFFF, int(philox[1]) & 0xFFFFFFFFFFFFFFFF)
+        keep.append(pa)
+        noise_p = C.cast(C.pointer(pa), C.c_void_p)          # HOST pointer, read during the call
     elif src == SRC_GIVEN:
         _require_cuda(x_next, "prev_sample")
         if x_next.dtype != torch.float32:

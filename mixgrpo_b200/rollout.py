@@ -23,7 +23,7 @@ import torch
 from . import coefs as _coefs
 from . import grpo as _grpo
 from . import ops as _ops
-from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX
 from .sampling_utils import DPMState, _dpm_order, _flash_schedule, _mode
 
 
@@ -43,6 +43,7 @@ class SamplerConfig:
     sample_strategy: str = "progressive"
     drop_last_sample: bool = False
     rounding: str = "auto"
+    inkernel_noise: bool = False             # draw SDE noise inside the step kernel when `noises[i]` is None (no randn launch)
 
 
 def sigma_schedule(sampling_steps: int, shift: float, device=None) -> torch.Tensor:
@@ -65,7 +66,7 @@ def window_mask(sampling_steps: int, timesteps_train: Sequence[int], training_st
 
 def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.Tensor, sigmas: torch.Tensor,
             determistic: Sequence[bool], cfg: SamplerConfig, noises: Optional[Sequence[Optional[torch.Tensor]]] = None,
-            want_x0: bool = False):
+            want_x0: bool = False, generator: Optional[torch.Generator] = None):
     """Batched equivalent of SU:61-155.  ``model(latents, sigma_float, step) -> model_output`` stands for the
     DiT forward (SU:62-82).  Returns ``(z_final, latents, all_latents (B,N+1,...), all_log_probs (B,N), sigmas)``
     where ``sigmas`` is the schedule actually used (rebuilt in Flash "post" mode, SU:33-54)."""
@@ -112,13 +113,16 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
         else:
             fam = _ops.FLOW if cfg.flow_grpo_sampling else _ops.DANCE
             k, _ = (_coefs.flow if cfg.flow_grpo_sampling else _coefs.dance)(sigmas, i, cfg.eta, mode, bf16_v)
+            ph = None
             if determistic[i]:
                 src, nz = SRC_DETERMINISTIC, None
+            elif nz is None and cfg.inkernel_noise:
+                src, ph = SRC_PHILOX, _ops.philox_from_generator(dev, v.numel(), generator)
             else:
                 src = SRC_NOISE
                 if nz is None:
-                    nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32)
-            _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, sde_solver=not determistic[i], out_x_next=out,
+                    nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32, generator=generator)
+            _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
                                           out_logp=logps_t[i], want_x0=keep_x0, round_like_torch=rnd)
             if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
                 dpm_state.update(x0)

@@ -26,7 +26,11 @@ import torch
 
 from . import coefs as _coefs
 from . import ops as _ops
-from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX
+
+#: draw SDE noise inside the step kernel (counter-based Philox, no randn launch, no noise tensor) when the caller
+#: supplies none; off by default so a drop-in run consumes torch's RNG stream exactly like torch.randn would
+INKERNEL_NOISE = os.environ.get("MIXGRPO_INKERNEL_NOISE", "0") == "1"
 
 #: rounding mode used when callers do not pass ``rounding=`` ("ref_cuda" | "ref_cpu" | "fp32")
 DEFAULT_ROUNDING = os.environ.get("MIXGRPO_ROUNDING", "ref_cuda")
@@ -86,13 +90,14 @@ def flow_grpo_step(
     generator: Optional[torch.Generator] = None,
     determistic: bool = False,
     *,
-    noise: Optional[torch.Tensor] = None,
+    noise=None,
     rounding: Optional[str] = None,
     return_mean: bool = True,
 ):
     """SU:157-210.  Returns ``(prev_sample, pred_original_sample, log_prob, prev_sample_mean,
     std_dev_t*sqrt(-dt))``.  ``return_mean=False`` skips writing the (unused by every reference
-    caller, TR:149, SU:85,118) mean tensor and returns None in its place."""
+    caller, TR:149, SU:85,118) mean tensor and returns None in its place.  ``noise``: a tensor (explicit noise),
+    ``"philox"`` (drawn inside the kernel from ``generator`` / the device default generator) or None (torch.randn)."""
     if prev_sample is not None and generator is not None:            # SU:180-184
         raise ValueError(
             "Cannot pass both generator and prev_sample. Please make sure that either `generator` or"
@@ -109,6 +114,10 @@ def flow_grpo_step(
         # stochastic branch needs it here
         if determistic:
             xn, x0, logp, mean = _ops.fused_step(_ops.FLOW, model_output, latents, k, src=SRC_DETERMINISTIC,
+                                                 want_mean=return_mean, round_like_torch=rnd)
+        elif (isinstance(noise, str) and noise == "philox") or (noise is None and INKERNEL_NOISE):
+            ph = _ops.philox_from_generator(model_output.device, model_output.numel(), generator)
+            xn, x0, logp, mean = _ops.fused_step(_ops.FLOW, model_output, latents, k, src=SRC_PHILOX, philox=ph,
                                                  want_mean=return_mean, round_like_torch=rnd)
         else:
             if noise is None:

@@ -454,3 +454,51 @@ def test_full_size_bit_exact_vs_reference_ops_on_device(B, S, dtype):
         lp16 = su.flow_grpo_step(v32.bfloat16(), x, ETA, sig, idx, xn)[2]
         rel = ((lp16 - lp.detach()).abs() / lp.detach().abs()).max().item()
         assert rel < 5e-3, rel          # bf16 quantisation of v moves the mean by <= 2^-9 relative: log-prob within 0.5 %
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_inkernel_philox_noise_matches_host_restatement(dtype):
+    """MIXGRPO_SRC_PHILOX: the SDE noise is drawn inside the step kernel as a pure function of (seed, offset, element).
+    Checked against the host restatement (oracle/philox_oracle.py, itself pinned by Random123 known answers) fed to the
+    oracle step as explicit noise; the device uses fast log/sincos, so a few values land on the other side of a bf16
+    rounding boundary — the rest is bit-exact."""
+    import numpy as np
+    from mixgrpo_b200 import coefs, ops
+    from mixgrpo_b200._cabi import SRC_PHILOX
+    from oracle import philox_oracle as P
+    d = _dev()
+    B, S, idx, seed, off = 3, 160, 6, 20261018, 40
+    x, v, _, _ = _inputs(B, S, dtype, seed=71)
+    nz = torch.from_numpy(P.normal(seed, off, B * S * 64)).view(B, S, 64).to(dtype)
+    ref = O.flow_step(v, x, ETA, SIG, idx, None, nz, False)
+    k, _ = coefs.flow(SIG, idx, ETA, "ref_cpu", dtype == torch.bfloat16)
+    out = ops.fused_step(ops.FLOW, v.to(d), x.to(d), k, src=SRC_PHILOX, philox=(seed, off), round_like_torch=True)
+    diff = (out[0].cpu() - ref[0]).abs()
+    scale = ref[4].item()
+    if dtype == torch.bfloat16:
+        assert (diff > 0).float().mean() < 2e-3                       # rare bf16 rounding flips of the noise
+        assert diff.max() <= scale * 2 ** -5                           # at most one bf16 ulp of |eps| <= 4
+    else:
+        assert diff.max() < 1e-5
+    assert torch.allclose(out[2].cpu(), ref[2], rtol=2e-4, atol=0)
+    # pure function of (seed, offset, element): the scalar path (misaligned view) draws the same numbers
+    base = torch.zeros(B * S * 64 + 1, device=d)
+    base[1:] = x.to(d).flatten()
+    out2 = ops.fused_step(ops.FLOW, v.to(d), base[1:].view(B, S, 64), k, src=SRC_PHILOX, philox=(seed, off), round_like_torch=True)
+    assert torch.equal(out2[0], out[0])
+    out3 = ops.fused_step(ops.FLOW, v.to(d), x.to(d), k, src=SRC_PHILOX, philox=(seed, off + 4), round_like_torch=True)
+    assert not torch.equal(out3[0], out[0])
+    # drop-in: noise="philox" consumes the generator's offset, so consecutive calls differ and re-seeding reproduces
+    from mixgrpo_b200 import sampling_utils as su
+    g = torch.Generator(device=d).manual_seed(5)
+    a1 = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, idx, None, generator=g, noise="philox")[0]
+    a2 = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, idx, None, generator=g, noise="philox")[0]
+    g.manual_seed(5)
+    a3 = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, idx, None, generator=g, noise="philox")[0]
+    assert not torch.equal(a1, a2) and torch.equal(a1, a3)
+    # statistics at full size: log-prob of the rollout sample ~ -1/2 - log s - log sqrt(2 pi)
+    xl = torch.randn(12, 4096, 64, device=d)
+    vl = torch.randn(12, 4096, 64, device=d).to(dtype)
+    lp = su.flow_grpo_step(vl, xl, ETA, SIG, idx, None, noise="philox")[2]
+    expect = -0.5 - np.log(scale) - 0.5 * np.log(2 * np.pi)
+    assert torch.allclose(lp.cpu(), torch.full((12,), float(expect)), atol=5e-3)

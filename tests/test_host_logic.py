@@ -152,3 +152,19 @@ def test_make_samples_slices_and_reward_stacking():
     assert torch.equal(single, torch.arange(4.0))                        # no process group: identity (TR:333-334)
     d = grpo.gather_rewards({"a": torch.ones(3)})
     assert list(d) == ["a"] and torch.equal(d["a"], torch.ones(3))
+
+
+def test_philox_oracle_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (zeros / ones / pi) pin the host restatement of the in-kernel
+    noise generator; the GPU test then pins the kernel to the host restatement."""
+    import numpy as np
+    from oracle import philox_oracle as P
+    z = np.zeros(1, dtype=np.uint64)
+    f = np.full(1, 0xffffffff, dtype=np.uint64)
+    assert [int(a[0]) for a in P.philox4x32_10(z, z, z, z, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(a[0]) for a in P.philox4x32_10(f, f, f, f, 0xffffffff, 0xffffffff)] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    pi = [np.array([w], dtype=np.uint64) for w in (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)]
+    assert [int(a[0]) for a in P.philox4x32_10(*pi, 0xa4093822, 0x299f31d0)] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    n = P.normal(7, 12, 1 << 18)
+    assert abs(n.mean()) < 5e-3 and abs(n.std() - 1) < 5e-3 and np.isfinite(n).all()
+    assert not np.array_equal(P.normal(7, 16, 64), n[:64]) and np.array_equal(P.normal(7, 12, 64), n[:64])
