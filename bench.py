@@ -139,6 +139,8 @@ class Workload:
         self.weights = torch.tensor([1.0, 0.5, 2.0], device=dev)
         self.stats_rows = torch.zeros(WINDOW, B, 4, device=dev)   # per (window step, sample): loss, policy, kl, clip_frac
         self.side = [torch.cuda.Stream(device=dev) for _ in range(WINDOW)]
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        self.gbuf = torch.empty(world * N_MODELS, B, device=dev)      # all-gathered rewards, rank-major rows
 
     def noises(self, window):
         nz = [None] * N_STEPS
@@ -147,10 +149,19 @@ class Workload:
         return nz
 
 
-def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=None, collectives=True, parallel=True):
+def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=None, collectives=True, parallel=True, comm=None):
     """One GRPO iteration's hot path through the public API (mixgrpo_b200.rollout / .grpo)."""
     from mixgrpo_b200 import grpo, rollout as R
     v_list = v_list if v_list is not None else w.v
+    cur0 = torch.cuda.current_stream(w.dev)
+    if comm is not None:
+        # pipelined collectives on a side branch, concurrent with the rollout: this step's reward all-gather and the
+        # PREVIOUS step's stats all-reduce (logging-only quantities, TR:427-437 / TR:586-600); joined before the policy
+        # updates overwrite the stats rows
+        comm.wait_stream(cur0)
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(w.gbuf, w.rewards)
+            dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)
     det = R.window_mask(N_STEPS, window)
     nz = [None] * N_STEPS
     for j, i in enumerate(window):
@@ -161,6 +172,8 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
         gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
         _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
     adv = grpo.compute_group_advantages(rew, B, w.weights)
+    if comm is not None:
+        cur0.wait_stream(comm)
     # the window's policy updates are independent of one another (TR:536-585 loops over them): one stream each, so
     # their kernels overlap; every (step, sample) owns its stats row -> no zeroing, no race, summed when logged
     cur = torch.cuda.current_stream(w.dev)
@@ -183,18 +196,30 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
 LAUNCHES_PER_STEP = 1 + N_STEPS + 1 + 2 * WINDOW  # all ours: trajectory seed + 25 sampler + 1 advantage + 4 x (policy fwd, policy bwd)
 
 
-def capture_step(w: Workload, window):
-    """The device part of a step as a CUDA graph (collectives stay outside the graph)."""
+def capture_step(w: Workload, window, comm=None):
+    """One whole step as a CUDA graph.  With ``comm`` (N > 1) the two NCCL collectives are captured too, on a side branch
+    concurrent with the rollout, so a step costs the host ONE graph launch; returns (graph, outputs, collectives_in_graph)."""
     s = torch.cuda.Stream(device=w.dev)
     s.wait_stream(torch.cuda.current_stream(w.dev))
     with torch.cuda.stream(s):
-        native_step(w, window, collectives=False)  # warm-up on the capture stream (allocations, workspaces, coef tables)
+        native_step(w, window, collectives=False, comm=comm)   # warm-up on the capture stream (allocations, workspaces, coef tables, NCCL)
     s.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g, stream=s):
-        out = native_step(w, window, collectives=False)
+    in_graph = comm is not None
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = native_step(w, window, collectives=False, comm=comm)
+    except Exception as e:  # noqa: BLE001  (NCCL capture unavailable: keep the collectives eager on a side stream)
+        if comm is None:
+            raise
+        print(f"[bench] NCCL graph capture failed ({type(e).__name__}: {e}); collectives stay eager", file=sys.stderr)
+        torch.cuda.synchronize(w.dev)
+        in_graph = False
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = native_step(w, window, collectives=False)
     torch.cuda.current_stream(w.dev).wait_stream(s)
-    return g, out
+    return g, out, in_graph
 
 
 def measure_roofline(dev, peak_gbs, peak_kind):
@@ -369,24 +394,23 @@ def run_native(args):
     states = GRPOTrainingStates(iters_per_group=25, group_size=WINDOW, max_timesteps=N_STEPS - 2, prog_overlap=True, prog_overlap_step=1)
     window = states.get_current_timesteps()
 
-    graph, (stats, logps, _) = capture_step(w, window)
-
     # The path's two tiny collectives (reward all-gather, stats all-reduce) feed logging only in the reference's
-    # group mode (TR:427-437, TR:586-600), so they run on a side stream: ordered after the step that produced their
-    # inputs, waited for before the next step overwrites them, and inside the timed region.
+    # group mode (TR:427-437, TR:586-600).  They are captured into the step's graph on a side branch that runs
+    # concurrently with the rollout (this step's rewards, the previous step's stats), so the host issues one graph
+    # launch per step at any N; if NCCL capture is unavailable they run eagerly on a side stream instead.
     main_stream = torch.cuda.current_stream(dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    graph, (stats, logps, _), coll_in_graph = capture_step(w, window, comm_stream)
 
     def step():
-        if world > 1:
+        if world > 1 and not coll_in_graph:
             main_stream.wait_stream(comm_stream)
         graph.replay()
-        if world > 1:
-            from mixgrpo_b200 import grpo
+        if world > 1 and not coll_in_graph:
             comm_stream.wait_stream(main_stream)
             with torch.cuda.stream(comm_stream):
-                grpo.gather_rewards(w.rewards)
-                grpo.reduce_step_stats(w.stats_rows)
+                dist.all_gather_into_tensor(w.gbuf, w.rewards)
+                dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)
 
     for _ in range(args.warmup):
         step()
@@ -402,7 +426,10 @@ def run_native(args):
         for _ in range(args.steps):
             step()
         if world > 1:
-            main_stream.wait_stream(comm_stream)      # the last step's collectives end inside the timed region
+            if coll_in_graph:
+                dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)   # the last step's stats (earlier ones were reduced one step late)
+            else:
+                main_stream.wait_stream(comm_stream)  # the last step's collectives end inside the timed region
         b.record()
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
@@ -412,7 +439,9 @@ def run_native(args):
             if rank == 0:
                 print(json.dumps({"profile_only": True, "steps": args.steps, "ms_per_step": ms / args.steps}), flush=True)
             if world > 1:
-                dist.destroy_process_group()
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                os._exit(0)
             return
         roof, kernels = measure_roofline(dev, peak, peak_kind) if rank == 0 else (None, None)
         if roof is not None:
@@ -436,7 +465,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
                                    "one prompt group per GPU", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
-                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group",
+                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream")),
                        "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
@@ -449,7 +478,13 @@ def run_native(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A live CUDA graph that holds captured NCCL kernels makes destroy_process_group() block at teardown (seen on
+        # this image: the line was printed, then the ranks hung).  Drain, rendezvous once more, and leave without it.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------ reference arm (CPU)
