@@ -400,17 +400,30 @@ def run_native(args):
     # launch per step at any N; if NCCL capture is unavailable they run eagerly on a side stream instead.
     main_stream = torch.cuda.current_stream(dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    graph, (stats, logps, _), coll_in_graph = capture_step(w, window, comm_stream)
+    graph, (stats, logps, _), coll_in_graph = capture_step(w, window, comm_stream if args.collectives == "graph" else None)
+    # eager mode: two graphs with their own stats rows, used alternately, so step k+1 never has to wait for step k's
+    # all-reduce to finish reading its rows — the collectives overlap the next step completely
+    graphs, rows = [graph], [w.stats_rows]
+    if world > 1 and not coll_in_graph:
+        w.stats_rows = torch.zeros_like(w.stats_rows)
+        g2, _, _ = capture_step(w, window, None)
+        graphs.append(g2)
+        rows.append(w.stats_rows)
+    done = [torch.cuda.Event() for _ in graphs]
+    counter = [0]
 
     def step():
+        k = counter[0] % len(graphs)
+        counter[0] += 1
         if world > 1 and not coll_in_graph:
-            main_stream.wait_stream(comm_stream)
-        graph.replay()
+            main_stream.wait_event(done[k])          # the collectives that read rows[k] two steps ago
+        graphs[k].replay()
         if world > 1 and not coll_in_graph:
             comm_stream.wait_stream(main_stream)
             with torch.cuda.stream(comm_stream):
                 dist.all_gather_into_tensor(w.gbuf, w.rewards)
-                dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)
+                dist.all_reduce(rows[k], op=dist.ReduceOp.AVG)
+                done[k].record(comm_stream)
 
     for _ in range(args.warmup):
         step()
@@ -443,7 +456,7 @@ def run_native(args):
                 dist.barrier()
                 os._exit(0)
             return
-        roof, kernels = measure_roofline(dev, peak, peak_kind) if rank == 0 else (None, None)
+        roof, kernels = measure_roofline(dev, peak, peak_kind) if (rank == 0 and not args.skip_e2e) else (None, None)
         if roof is not None:
             roof["traffic"], roof["traffic_note"] = load_ncu_traffic()
     ms_per_step = max_over_ranks(ms / args.steps, dev)
@@ -451,6 +464,13 @@ def run_native(args):
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
     loss_host = float(stats.sum(dim=(0, 1))[0].item())
 
+    if args.skip_e2e:
+        if rank == 0:
+            print(json.dumps({"tuning_only": True, "n_gpus": world, "ms_per_step": ms_per_step, "value": value, "collectives": args.collectives,
+                              "in_graph": coll_in_graph}), flush=True)
+        if world > 1:
+            torch.cuda.synchronize(dev); dist.barrier(); os._exit(0)
+        return
     e2e_s, h2d, d2h, e2e_loss = e2e_run(w, window, max(3, min(args.steps, 20)), 3)
     e2e_s = max_over_ranks(e2e_s, dev)
     e2e_value = total_bytes / e2e_s / 1e9
@@ -465,7 +485,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
                                    "one prompt group per GPU", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
-                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream")),
+                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
                        "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
@@ -553,6 +573,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collectives", default="eager", choices=["graph", "eager"], help="N>1: capture the two NCCL collectives in the step graph, or issue them eagerly on a side stream")
+    ap.add_argument("--skip-e2e", action="store_true", help="(tuning only) skip the e2e and roofline legs")
     ap.add_argument("--profile-only", action="store_true", help="setup + warm-up + K timed steps between cudaProfilerStart/Stop, then exit (for ncu)")
     args = ap.parse_args()
     if args.steps is None:
