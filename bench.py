@@ -477,14 +477,14 @@ def run_native(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_step(1, 1)
+        cpu = cpu_reference_step(None, 1, budget_s=12.0)
     if rank == 0:
         line = {
             "metric": "sampler-step latent GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
-                                   "one prompt group per GPU", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
+                                   "one prompt group per GPU", "io_dtypes": "model_output/noise bf16 in, latents/trajectory/log-prob fp32, grad bf16; arithmetic fp32", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
                        "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
                        "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
@@ -508,7 +508,7 @@ def run_native(args):
 
 
 # ------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_step(steps: int, warmup: int):
+def cpu_reference_step(steps, warmup: int, budget_s: float = 0.0):
     """The reference's algorithm for the same step on the host cores (oracle = torch-CPU restatement pinned
     bit-exact to the reference's own functions).  Returns the cpu_baseline object."""
     from oracle import grpo_oracle as GO
@@ -536,11 +536,18 @@ def cpu_reference_step(steps: int, warmup: int):
             tot += float(loss.detach())
         return tot
 
+    torch.set_num_threads(os.cpu_count() or 1)          # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        loss = one()
+    if steps is None:                                   # bounded sample: whole steps until ~budget_s of CPU work
+        steps = 0
+        while steps < 200 and (steps == 0 or time.perf_counter() - t0 < budget_s):
+            loss = one()
+            steps += 1
+    else:
+        for _ in range(steps):
+            loss = one()
     dt = (time.perf_counter() - t0) / steps
     gbs = algorithmic_bytes_per_step() / dt / 1e9
     return {"value": round(gbs, 4), "unit": "GB/s", "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
@@ -558,7 +565,7 @@ def run_reference(args):
     cpu = cpu_reference_step(args.steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "sampler-step latent GB/s", "value": cpu["value"], "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cpu["s_per_step"] * 1e3, 2), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 model_output/noise, f32 latents+math", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1])",
                        "device": "host CPU cores (reference PyTorch path)"},
             "rollout_steps_per_s": round(B * N_STEPS / cpu["s_per_step"], 2), "cpu_baseline": cpu,

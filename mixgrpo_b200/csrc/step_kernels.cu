@@ -196,8 +196,9 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
   }
 }
 
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
-__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || WMEAN || !VECTOR || (FAM == kDance && SDE)) ? 4 : (SRC == MIXGRPO_SRC_PHILOX ? 5 : 6))
+// OUT (compile time): 0 = neither x0 nor mean is stored (the rollout driver's steps: x0 is dead code), 1 = x0, 2 = x0 + mean
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT>
+__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE)) ? 4 : (SRC == MIXGRPO_SRC_PHILOX ? 5 : 6))
 step_kernel(const __grid_constant__ StepParams p) {
   pdl_prologue();
   const int b = blockIdx.y;
@@ -237,7 +238,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
     if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
 
-    float xn[kVec], x0[kVec], mu[WMEAN ? kVec : 2];
+    float xn[kVec], x0[OUT >= 1 ? kVec : 2], mu[OUT == 2 ? kVec : 2];
 #pragma unroll
     for (int j = 0; j < kVec; j += 2) {           // pair-wise: short live ranges, packed bf16 rounding
       const float v2[2] = {v[j], v[j + 1]}, x2[2] = {x[j], x[j + 1]}, a2[2] = {a[j], a[j + 1]};
@@ -245,8 +246,8 @@ step_kernel(const __grid_constant__ StepParams p) {
       float xn2[2], x02[2], mu2[2], dd2[2];
       tile_math<FAM, (SRC == MIXGRPO_SRC_PHILOX ? MIXGRPO_SRC_NOISE : SRC), ORDER, RND, SDE>(p.k, v2, x2, a2, m12, m22, xn2, x02, mu2, dd2);
       xn[j] = xn2[0]; xn[j + 1] = xn2[1];
-      x0[j] = x02[0]; x0[j + 1] = x02[1];
-      if constexpr (WMEAN) { mu[j] = mu2[0]; mu[j + 1] = mu2[1]; }
+      if constexpr (OUT >= 1) { x0[j] = x02[0]; x0[j + 1] = x02[1]; }
+      if constexpr (OUT == 2) { mu[j] = mu2[0]; mu[j + 1] = mu2[1]; }
       if constexpr (VECTOR) {
         acc += dd2[0] + dd2[1];
       } else {                                    // ragged tail: mask scalars beyond the sample
@@ -257,8 +258,8 @@ step_kernel(const __grid_constant__ StepParams p) {
     if constexpr (SRC != MIXGRPO_SRC_GIVEN) {
       if (p.x_out) store_tile<VECTOR>(p.x_out + (long long)b * p.out_bs, off, n, xn);
     }
-    if (p.x0_out) store_tile<VECTOR>(p.x0_out + (long long)b * n, off, n, x0);
-    if constexpr (WMEAN) store_tile<VECTOR>(p.mean_out + (long long)b * n, off, n, mu);
+    if constexpr (OUT >= 1) store_tile<VECTOR>(p.x0_out + (long long)b * n, off, n, x0);
+    if constexpr (OUT == 2) store_tile<VECTOR>(p.mean_out + (long long)b * n, off, n, mu);
   }
   if (p.logp_out == nullptr) return;
 
@@ -312,28 +313,32 @@ int g_use_pdl = 1;                                      // bench knob (key 1): p
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, bool WMEAN>
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT>
 static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
   dim3 grid((unsigned)ctas, (unsigned)p.B);
-  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, WMEAN>, grid, kThreads, 0, st, p);
+  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT>, grid, kThreads, 0, st, p);
   return (int)cudaGetLastError();
+}
+
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, int OUT>
+static int pick_vec(StepParams& p, bool vec_ok, cudaStream_t st) {
+  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, OUT>(p, st);
+  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT>(p, st);
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE>
 static int pick_width(StepParams& p, int64_t, bool vec_ok, cudaStream_t st) {
-  if constexpr (FAM == kDpm) {                     // dpm_step never returns the mean (SU:385)
+  if (p.mean_out && !p.x0_out) return MIXGRPO_EINVAL;     // the mean is only offered together with x0 (SU:210)
+  if constexpr (FAM == kDpm) {                             // dpm_step never returns the mean (SU:385)
     if (p.mean_out) return MIXGRPO_EINVAL;
-    if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, false>(p, st);
-    return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, false>(p, st);
+    if (p.x0_out) return pick_vec<FAM, VT, NT, SRC, ORDER, RND, SDE, 1>(p, vec_ok, st);
+    return pick_vec<FAM, VT, NT, SRC, ORDER, RND, SDE, 0>(p, vec_ok, st);
   } else {
-    if (p.mean_out) {
-      if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, true>(p, st);
-      return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, true>(p, st);
-    }
-    if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, false>(p, st);
-    return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, false>(p, st);
+    if (p.mean_out) return pick_vec<FAM, VT, NT, SRC, ORDER, RND, SDE, 2>(p, vec_ok, st);
+    if (p.x0_out) return pick_vec<FAM, VT, NT, SRC, ORDER, RND, SDE, 1>(p, vec_ok, st);
+    return pick_vec<FAM, VT, NT, SRC, ORDER, RND, SDE, 0>(p, vec_ok, st);
   }
 }
 
