@@ -4,7 +4,8 @@
 // about moving bytes: 256-bit LDG/STG (sm_100 adds .v8.f32 / LDG.E.256) so that one thread owns 8
 // consecutive latent scalars in every stream — 32 B of fp32, 16 B of bf16 — and every warp-level
 // request covers whole 128-B lines with all sectors used; streaming (no-L1-allocate) hints; a
-// deterministic warp-shuffle → shared → last-CTA reduction for the per-sample log-prob.
+// deterministic warp-shuffle → shared → packed fixed-point atomic reduction for the per-sample log-prob;
+// programmatic dependent launch so chained kernels overlap their tails; counter-based in-kernel noise.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -144,21 +145,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// Sum over the CTA, result valid in every thread of warp 0 (fixed tree => bitwise reproducible).
-__device__ __forceinline__ float block_sum(float v, float* s_warp /* [kThreads/32] */) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-  if (warp == 0) {
-    t = lane < (kThreads / 32) ? s_warp[lane] : 0.f;
-    t = warp_sum(t);
-  }
-  __syncthreads();
-  return t;
 }
 
 // ---------------------------------------------------------------- clipped-ratio GRPO loss, one sample
