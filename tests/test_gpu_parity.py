@@ -502,3 +502,59 @@ def test_inkernel_philox_noise_matches_host_restatement(dtype):
     lp = su.flow_grpo_step(vl, xl, ETA, SIG, idx, None, noise="philox")[2]
     expect = -0.5 - np.log(scale) - 0.5 * np.log(2 * np.pi)
     assert torch.allclose(lp.cpu(), torch.full((12,), float(expect)), atol=5e-3)
+
+
+def test_randomised_schedules_shapes_and_etas_vs_oracle():
+    """Property sweep: random sampling-step counts, shifts, etas, step indices, batch sizes and token counts
+    (vector-sized and ragged) for the three operator families, bf16 and fp32, against the CPU oracle."""
+    import random
+    import types as _types
+    from mixgrpo_b200 import sampling_utils as su
+    rnd = random.Random(20261018)
+    d = _dev()
+    for trial in range(48):
+        n_steps = rnd.choice([4, 10, 16, 25, 50])
+        shift = rnd.choice([1.0, 2.0, 3.0, 5.5])
+        eta = rnd.choice([0.1, 0.3, 0.7, 1.0])
+        sig = O.sd3_time_shift(shift, torch.linspace(1, 0, n_steps + 1))
+        idx = rnd.randrange(0, n_steps)
+        B = rnd.choice([1, 2, 5, 12])
+        S = rnd.choice([1, 3, 32, 45, 256, 333])
+        dtype = rnd.choice([torch.bfloat16, torch.float32])
+        g = torch.Generator().manual_seed(trial)
+        x = torch.randn(B, S, 64, generator=g)
+        v = torch.randn(B, S, 64, generator=g).to(dtype)
+        fam = trial % 3
+        if fam == 0:
+            eps = torch.randn(B, S, 64, generator=g).to(dtype)
+            det = rnd.random() < 0.3
+            out = su.flow_grpo_step(v.to(d), x.to(d), eta, sig, idx, None, determistic=det, noise=eps.to(d), rounding="ref_cpu")
+            ref = O.flow_step(v, x, eta, sig, idx, None, eps, det)
+            assert torch.equal(out[0].cpu(), ref[0]) and torch.equal(out[1].cpu(), ref[1]) and torch.equal(out[3].cpu(), ref[3]), (trial, "flow")
+            fin = torch.isfinite(ref[2])
+            assert torch.allclose(out[2].cpu()[fin], ref[2][fin], rtol=2e-5, atol=1e-6), (trial, "flow logp")
+        elif fam == 1:
+            nz = torch.randn(B, S, 64, generator=g)
+            sde = rnd.random() < 0.7
+            out = su.dance_grpo_step(v.to(d), x.to(d), eta, sig, idx, None, True, sde, noise=nz.to(d), rounding="ref_cpu")
+            ref = O.dance_step(v, x, eta, sig, idx, None, nz, True, sde)
+            assert torch.equal(out[0].cpu(), ref[0]) and torch.equal(out[1].cpu(), ref[1]), (trial, "dance")
+            fin = torch.isfinite(ref[2])
+            assert torch.allclose(out[2].cpu()[fin], ref[2][fin], rtol=1e-4, atol=1e-9), (trial, "dance logp")
+        else:
+            if idx == 0 or idx >= n_steps - 1:
+                idx = max(1, min(n_steps - 2, idx))
+            stype = rnd.choice(["midpoint", "heun"])
+            args = _types.SimpleNamespace(dpm_algorithm_type="dpmsolver++", dpm_solver_type=stype, dpm_solver_order=2)
+            m1 = torch.randn(B, S, 64, generator=g)
+            nz = torch.randn(B, S, 64, generator=g)
+            sde = rnd.random() < 0.5
+            st, oh = su.DPMState(order=2), O.History(2)
+            st.model_outputs, st.lower_order_nums = [None, m1.to(d)], 1
+            oh.model_outputs, oh.lower_order_nums = [None, m1], 1
+            out = su.dpm_step(args, v.to(d), x.to(d), idx, sig[:-1], sig, dpm_state=st, variance_noise=nz.to(d), sde_solver=sde, rounding="ref_cpu")
+            ref = O.dpm_step(v, x, idx, n_steps, sig, algo="dpmsolver++", solver_order=2, solver_type=stype, history=oh, noise=nz, sde_solver=sde)
+            assert torch.equal(out[1].cpu(), ref[1]), (trial, "dpm x0")
+            assert _rel(out[0].cpu(), ref[0]) < 1e-5, (trial, "dpm prev")
+            if sde:
+                assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-4, atol=0), (trial, "dpm logp")

@@ -168,3 +168,19 @@ def test_philox_oracle_known_answers():
     n = P.normal(7, 12, 1 << 18)
     assert abs(n.mean()) < 5e-3 and abs(n.std() - 1) < 5e-3 and np.isfinite(n).all()
     assert not np.array_equal(P.normal(7, 16, 64), n[:64]) and np.array_equal(P.normal(7, 12, 64), n[:64])
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the reference's CPU path via the oracle) works on a CPU-only box and prints the contract keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=str(root))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
