@@ -43,8 +43,10 @@ def test_sass_is_sm100a_with_256bit_accesses():
     lib = str(_build.build())
     elf = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2mg11step_kernelILi0E13__nv_bfloat16S1_Li0ELi1ELb1ELb0ELb1ELb0EEEvNS_10StepParamsE", lib],
-                          capture_output=True, text=True).stdout
+    usage = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    names = [ln.split()[1].rstrip(":") for ln in usage.splitlines() if ln.strip().startswith("Function") and "step_kernelILi0E13__nv_bfloat16S1_Li0E" in ln]
+    assert names, "no flow/bf16/SDE step_kernel instantiation in the library"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", names[0], lib], capture_output=True, text=True).stdout
     assert ".256" in sass and "LDG" in sass and "STG" in sass
 
 
