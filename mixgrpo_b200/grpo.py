@@ -31,6 +31,18 @@ def stack_rewards(rewards: RewardsLike) -> Tuple[torch.Tensor, Optional[List[str
     return (r.reshape(1, -1) if r.dim() == 1 else r), None
 
 
+def gather_tensor(tensor: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Drop-in for TR:332-338: all-gather a ``[local_B, ...]`` tensor and concatenate along dim 0 in rank order (one
+    ``all_gather_into_tensor`` instead of a list all-gather + ``torch.cat``); identity without a process group."""
+    if not dist.is_available() or not dist.is_initialized():
+        return tensor
+    world = dist.get_world_size(group)
+    t = tensor.contiguous()
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out
+
+
 def gather_rewards(rewards: RewardsLike, group: Optional[dist.ProcessGroup] = None) -> RewardsLike:
     """Replacement for the per-model ``gather_tensor`` list all-gathers (TR:332-338, TR:417-425): ONE
     ``all_gather_into_tensor`` of the ``[n_models, local_B]`` matrix.  Returns the same container type

@@ -34,6 +34,7 @@ def _worker(rank, world, port, q):
         ok = all(torch.equal(gathered[k], ref[k]) for k in local) and list(gathered) == list(local)
         flat = grpo.gather_rewards(local["hps"])
         ok = ok and torch.equal(flat, ref["hps"])
+        ok = ok and torch.equal(grpo.gather_tensor(local["pick"]), ref["pick"])          # TR:332-338 drop-in
         # rank-local group statistics: this rank's slice of the gathered vector gives back its own advantages
         adv_local = GO.group_advantages(local, 12, {"hps": 1.0, "pick": 0.5, "ir": 2.0})
         adv_from_gather = GO.group_advantages({k: v[rank * 12:(rank + 1) * 12] for k, v in gathered.items()}, 12, {"hps": 1.0, "pick": 0.5, "ir": 2.0})
