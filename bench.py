@@ -233,6 +233,8 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     vs = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(ns)]
     es = [torch.randn(B, S, C, device=dev, generator=g).bfloat16() for _ in range(ns)]
     outs = [torch.empty(B, S, C, device=dev) for _ in range(ns)]
+    x0s = [torch.empty(B, S, C, device=dev) for _ in range(ns)]      # every output stream rotates too (nothing stays hot in L2)
+    gvs = [torch.empty(B, S, C, device=dev, dtype=torch.bfloat16) for _ in range(ns)]
     lps = torch.empty(ns, B, device=dev)
     glp = torch.randn(B, device=dev)
     sig = torch.linspace(1, 0, N_STEPS + 1)
@@ -242,7 +244,7 @@ def measure_roofline(dev, peak_gbs, peak_kind):
 
     def run(kind, i):
         if kind == "sde_x0":
-            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, round_like_torch=True)
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], round_like_torch=True)
         elif kind == "sde":
             ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=False, round_like_torch=True)
         elif kind == "ode":
@@ -250,9 +252,9 @@ def measure_roofline(dev, peak_gbs, peak_kind):
         elif kind == "train_fwd":
             ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_GIVEN, x_next=outs[(i + 1) % ns], out_logp=lps[i], want_x0=False, round_like_torch=True)
         elif kind == "bwd":
-            ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True)
+            ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True, out=gvs[i])
         elif kind == "sde_x0_philox":      # noise drawn in the kernel: no noise tensor is read (and none was generated)
-            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_PHILOX, philox=(1234, 4 * i), out_x_next=outs[i], out_logp=lps[i], want_x0=True, round_like_torch=True)
+            ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_PHILOX, philox=(1234, 4 * i), out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], round_like_torch=True)
 
     res = {}
     s = torch.cuda.Stream(device=dev)

@@ -86,7 +86,8 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                m1: Optional[torch.Tensor] = None, m2: Optional[torch.Tensor] = None, order: int = 1,
                sde_solver: bool = True, out_x_next: Optional[torch.Tensor] = None, want_x0: bool = True,
                want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
-               out_logp: Optional[torch.Tensor] = None, philox: Optional[Tuple[int, int]] = None):
+               out_logp: Optional[torch.Tensor] = None, philox: Optional[Tuple[int, int]] = None,
+               out_x0: Optional[torch.Tensor] = None):
     """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
     requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in."""
     global launch_count
@@ -152,7 +153,14 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                 raise ValueError("mixgrpo_b200: out_x_next must be fp32, same shape, contiguous per sample")
             out = out_x_next
             out_p, out_bs = out.data_ptr(), (out.stride(0) if B > 1 else n)
-    x0 = torch.empty(v.shape, dtype=torch.float32, device=dev) if want_x0 else None
+    x0 = None
+    if want_x0:
+        if out_x0 is not None:
+            if out_x0.dtype != torch.float32 or out_x0.shape != v.shape or not out_x0.is_contiguous():
+                raise ValueError("mixgrpo_b200: out_x0 must be a contiguous fp32 tensor of the model output's shape")
+            x0 = out_x0
+        else:
+            x0 = torch.empty(v.shape, dtype=torch.float32, device=dev)
     mean = torch.empty(v.shape, dtype=torch.float32, device=dev) if want_mean else None
     logp = None
     if want_logp:
@@ -185,7 +193,7 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
 
 
 def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, grad_logp: torch.Tensor,
-                     coefs: StepCoefs, round_like_torch: bool = False) -> torch.Tensor:
+                     coefs: StepCoefs, round_like_torch: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """grad of sum_b grad_logp[b]*logp[b] w.r.t. model_output; dtype = model_output.dtype."""
     global launch_count
     lib = _cabi.lib()
@@ -199,7 +207,9 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
     g = grad_logp.to(torch.float32).contiguous()
     if g.numel() != B:
         raise ValueError("mixgrpo_b200: grad_log_prob must have one entry per sample")
-    grad_v = torch.empty_like(v)
+    grad_v = out if out is not None else torch.empty_like(v)
+    if grad_v.dtype != v.dtype or grad_v.shape != v.shape or not grad_v.is_contiguous():
+        raise ValueError("mixgrpo_b200: `out` must match model_output's dtype/shape and be contiguous")
     flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
     with torch.cuda.device(v.device):
         rc = lib.mixgrpo_logprob_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, g.data_ptr(),
