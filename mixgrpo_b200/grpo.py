@@ -156,3 +156,43 @@ def reduce_step_stats(stats_accum: torch.Tensor, group: Optional[dist.ProcessGro
             dist.all_reduce(stats_accum, op=dist.ReduceOp.SUM, group=group)
             stats_accum /= dist.get_world_size(group)
     return stats_accum
+
+
+# ----------------------------------------------------------------------------------------------- partitioning
+def partition_prompts(n_prompts: int, rank: int, world: int, drop_last: bool = False) -> List[int]:
+    """Which prompts (= prompt groups: each prompt is repeated ``num_generations`` times, TR:368-384) a rank owns:
+    ``rank, rank + world, ...`` — the order of ``DistributedSampler(shuffle=False)`` (TR:737-749), padded by wrapping
+    around unless ``drop_last``.  Groups never cross ranks, so group statistics stay rank-local (TR:443-461) and the
+    rollout needs no collective."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    if drop_last:
+        total = (n_prompts // world) * world
+        idx = list(range(total))
+    else:
+        total = ((n_prompts + world - 1) // world) * world
+        idx = list(range(n_prompts))
+        idx += idx[: total - n_prompts] if n_prompts else []
+    return idx[rank:total:world]
+
+
+def split_group_slice(values: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Extended mode: a prompt group split ACROSS ranks (e.g. group 24 over 8 GPUs = 3 samples each).
+    ``values`` is a rank-major gathered vector ``[world * local_B]`` (what ``gather_tensor`` returns); the rank's own
+    slice is returned."""
+    local = values.shape[-1] // world
+    return values[..., rank * local:(rank + 1) * local]
+
+
+def compute_group_advantages_split(rewards: RewardsLike, num_generations: int,
+                                   reward_weights: Optional[Union[Dict[str, float], Sequence[float]]] = None,
+                                   trimmed_ratio: float = 0.0, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Extended mode: groups of ``num_generations`` samples laid out consecutively in the rank-major GATHERED order, so a
+    group may span several ranks.  One all-gather of the reward matrix, the group kernel over the gathered matrix
+    (``world * local_B`` scalars per model), then this rank's slice.  With whole groups per rank it equals
+    ``compute_group_advantages`` on the local rewards."""
+    gathered = gather_rewards(rewards, group)
+    adv = compute_group_advantages(gathered, num_generations, reward_weights, trimmed_ratio)
+    if dist.is_available() and dist.is_initialized():
+        return split_group_slice(adv, dist.get_rank(group), dist.get_world_size(group)).contiguous()
+    return adv

@@ -39,6 +39,16 @@ def _worker(rank, world, port, q):
         adv_local = GO.group_advantages(local, 12, {"hps": 1.0, "pick": 0.5, "ir": 2.0})
         adv_from_gather = GO.group_advantages({k: v[rank * 12:(rank + 1) * 12] for k, v in gathered.items()}, 12, {"hps": 1.0, "pick": 0.5, "ir": 2.0})
         ok = ok and torch.equal(adv_local, adv_from_gather)
+        # extended mode: ONE group of 24 split over the 2 ranks (12 each): statistics come from the gathered vector
+        adv_full = GO.group_advantages(gathered["hps"], 24)
+        mine = grpo.split_group_slice(adv_full, rank, world)
+        ok = ok and mine.shape == (12,) and torch.equal(mine, adv_full[rank * 12:(rank + 1) * 12])
+        ok = ok and not torch.equal(mine, GO.group_advantages(local["hps"], 12))          # differs from rank-local statistics
+        # prompt partition: DistributedSampler(shuffle=False) order, padded by wrap-around
+        from torch.utils.data import DistributedSampler
+        for n_prompts in (7, 8, 1):
+            ds = list(DistributedSampler(list(range(n_prompts)), num_replicas=world, rank=rank, shuffle=False))
+            ok = ok and grpo.partition_prompts(n_prompts, rank, world) == ds
         stats = torch.tensor([1.0, 2.0, 3.0, 4.0]) * (rank + 1)
         red = grpo.reduce_step_stats(stats.clone())
         want = torch.tensor([1.0, 2.0, 3.0, 4.0]) * (sum(range(1, world + 1)) / world)

@@ -558,3 +558,21 @@ def test_randomised_schedules_shapes_and_etas_vs_oracle():
             assert _rel(out[0].cpu(), ref[0]) < 1e-5, (trial, "dpm prev")
             if sde:
                 assert torch.allclose(out[2].cpu(), ref[2], rtol=1e-4, atol=0), (trial, "dpm logp")
+
+
+def test_extended_mode_group_split_across_ranks_single_process():
+    """SURVEY §8e extended mode without a process group: the 'gathered' matrix is just the local one, so
+    compute_group_advantages_split must equal compute_group_advantages; and slicing a gathered result reproduces the
+    oracle's advantages for a group of 24 held as 8 x 3."""
+    from mixgrpo_b200 import grpo
+    d = _dev()
+    g = torch.Generator().manual_seed(8)
+    r = {"a": torch.randn(24, generator=g), "b": torch.randn(24, generator=g)}
+    w = {"a": 1.0, "b": 0.3}
+    rd = {k: v.to(d) for k, v in r.items()}
+    full = grpo.compute_group_advantages_split(rd, 24, w)
+    assert torch.equal(full, grpo.compute_group_advantages(rd, 24, w))
+    ref = GO.group_advantages(r, 24, w)
+    assert torch.allclose(full.cpu(), ref, atol=2e-6)
+    for rank in range(8):
+        assert torch.allclose(grpo.split_group_slice(full, rank, 8).cpu(), ref[rank * 3:(rank + 1) * 3], atol=2e-6)
