@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MIXGRPO_ABI_VERSION 1
+#define MIXGRPO_ABI_VERSION 2
 
 /* element type of model_output / noise / grad_model_output */
 enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
@@ -103,7 +103,8 @@ int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
 /* ABI / build introspection. */
 int mixgrpo_abi_version(void);
 const char* mixgrpo_build_info(void);          /* e.g. "sm_100a nvcc 12.9 ..." (static string) */
-int mixgrpo_set_tuning(int key, int value);    /* bench-only knobs (0: max CTAs/sample, 1: PDL on/off); returns previous value or <0 */
+int mixgrpo_set_tuning(int key, int value);    /* knobs (0: max CTAs/sample, 1: PDL on/off, 2: peer-wait timeout in ms, 0 = forever);
+                                                  returns the previous value or <0 */
 const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGetErrorString for >0) */
 
 /* ---- fused sampler step + Gaussian transition log-prob ---------------------------------------
@@ -209,6 +210,53 @@ int mixgrpo_group_advantages(const float* rewards, const float* weights, int n_m
 int mixgrpo_grpo_loss(const float* new_logp, const float* old_logp, const float* advantages,
                       int64_t B, double clip_range, double adv_clip_max, double kl_coeff, double denom,
                       float* stats_out, float* grad_new_logp, float* stats_accum, void* stream);
+
+/* ---- fused peer-memory exchange: reward gather + advantages, logging all-reduce (one node, NVLink) ----
+ * The path's only collective as ONE kernel per exchange instead of NCCL + a compute launch:
+ *   mixgrpo_peer_gather_advantages  replaces gather_tensor per reward model (TR:332-338, TR:417-425) AND the
+ *                                   advantage computation (TR:439-501): every rank pushes its [n_models, local_B]
+ *                                   rewards into every peer's region with st.global over NVLink, publishes a
+ *                                   sequence flag (st.release.sys), waits for the peers' flags (ld.acquire.sys) and
+ *                                   computes its advantages from the gathered matrix in the same CTA.
+ *   mixgrpo_peer_allreduce          replaces the all_reduce(AVG)+.item() pairs of TR:586-600 for <= 64 floats:
+ *                                   contributions are summed in rank order, so every rank gets the same bits.
+ * A "region" is mixgrpo_peer_region_bytes(world, cap_floats) bytes of cudaMalloc'ed memory per rank
+ * (cap_floats >= n_models*local_B), created with _alloc (which also returns a 64-byte CUDA IPC handle to ship to
+ * the peers by any host channel, e.g. torch.distributed.all_gather_object) and mapped by peers with _open.
+ * regions_host[q] is rank q's region as mapped in the CALLING process (its own allocation at [rank]).  All ranks
+ * must issue the same sequence of exchange calls (collective semantics); the call counter lives in the region, so
+ * the launches are CUDA-graph capturable.  A wait that exceeds the timeout (mixgrpo_set_tuning key 2, default
+ * 30 s) sets the region's status word and yields NaN outputs instead of hanging the GPU.
+ * Several "ranks" may live on ONE device (regions_host = plain device pointers, one stream per rank): that is how
+ * the single-GPU parity tests drive the protocol. */
+#define MIXGRPO_PEER_MAX_WORLD 16
+#define MIXGRPO_PEER_HANDLE_BYTES 64
+
+/* which columns form a group */
+enum {
+  MIXGRPO_ADV_GROUP_LOCAL = 0,  /* consecutive runs of num_generations of THIS rank's samples (TR:443-461)            */
+  MIXGRPO_ADV_GROUP_SPLIT = 1,  /* consecutive runs in the rank-major gathered order: a group may span ranks (§8e)    */
+  MIXGRPO_ADV_GLOBAL = 2        /* no groups: statistics of the whole gathered vector, one model (TR:495-499)         */
+};
+
+int64_t mixgrpo_peer_region_bytes(int world, int64_t cap_floats);
+int mixgrpo_peer_region_alloc(int world, int64_t cap_floats, void** region_out, void* ipc_handle_out /* 64 B or NULL */);
+int mixgrpo_peer_region_open(const void* ipc_handle, void** region_out);
+int mixgrpo_peer_region_close(void* region);   /* a region obtained from _open  */
+int mixgrpo_peer_region_free(void* region);    /* a region obtained from _alloc */
+/* synchronising debug read of (gather calls completed, all-reduce calls completed, status: 1 = a wait timed out) */
+int mixgrpo_peer_region_status(const void* region, int* seq_gather_host, int* seq_reduce_host, int* status_host);
+
+/*   rewards [n_models, local_B] fp32 (this rank), weights [n_models] or NULL (single model)
+ *   gathered_out [n_models, world*local_B] fp32 or NULL: column q*local_B + b = rank q's sample b (torch.cat order)
+ *   advantages [local_B] fp32: this rank's samples; entries outside a whole group are 0 (TR:445) */
+int mixgrpo_peer_gather_advantages(void* const* regions_host, int rank, int world, int64_t cap_floats,
+                                   const float* rewards, const float* weights, int n_models, int64_t local_B,
+                                   int num_generations, int trim_size, int mode, float* gathered_out,
+                                   float* advantages, void* stream);
+/*   values [count <= 64] fp32, reduced in place: sum over ranks (in rank order), divided by world when average != 0 */
+int mixgrpo_peer_allreduce(void* const* regions_host, int rank, int world, int64_t cap_floats, float* values,
+                           int count, int average, void* stream);
 
 /* ---- layout helpers either side of the path ----------------------------------------------------
  * mixgrpo_pack_latents    (B,C,H,W) -> (B,(H/2)(W/2),4C)     TR:94-99   (src dtype bf16|f32 -> same)

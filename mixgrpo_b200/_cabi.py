@@ -15,7 +15,9 @@ F32, BF16 = 0, 1
 SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC, SRC_PHILOX = 0, 1, 2, 3
 FLAG_ROUND_LIKE_TORCH = 1
 FLAG_PDL_EARLY_LOADS = 2
-ABI_VERSION = 1
+ADV_GROUP_LOCAL, ADV_GROUP_SPLIT, ADV_GLOBAL = 0, 1, 2
+PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
+ABI_VERSION = 2
 
 
 class StepCoefs(C.Structure):
@@ -57,6 +59,14 @@ SIGNATURES = {
     "mixgrpo_grpo_loss": (_I, [_P, _P, _P, _I64, _D, _D, _D, _D, _P, _P, _P, _P]),
     "mixgrpo_pack_latents": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P]),
     "mixgrpo_unpack_latents": (_I, [_P, _P, _I, _I64, _I, _I, _I, _F, _F, _P]),
+    "mixgrpo_peer_region_bytes": (_I64, [_I, _I64]),
+    "mixgrpo_peer_region_alloc": (_I, [_I, _I64, C.POINTER(_P), _P]),
+    "mixgrpo_peer_region_open": (_I, [_P, C.POINTER(_P)]),
+    "mixgrpo_peer_region_close": (_I, [_P]),
+    "mixgrpo_peer_region_free": (_I, [_P]),
+    "mixgrpo_peer_region_status": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "mixgrpo_peer_gather_advantages": (_I, [C.POINTER(_P), _I, _I, _I64, _P, _P, _I, _I64, _I, _I, _I, _P, _P, _P]),
+    "mixgrpo_peer_allreduce": (_I, [C.POINTER(_P), _I, _I, _I64, _P, _I, _I, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

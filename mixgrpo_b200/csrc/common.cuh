@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/mixgrpo_b200.h"
 
@@ -124,6 +125,9 @@ __device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned lo
 // cuBLAS) the attribute is inert and ordering is the ordinary stream order.  Measured: -0.4 us per chained launch,
 // -1.1 us with early loads (profiles/r01_design_space.md).
 extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_kernels.cu
+}  // namespace mg
+int mixgrpo_peer_set_timeout_ms(int ms);   // mixgrpo_set_tuning key 2, defined in peer_kernels.cu
+namespace mg {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

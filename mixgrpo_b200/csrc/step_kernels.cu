@@ -401,6 +401,7 @@ extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
+  if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
   if (key == 1) {
     if (value != 0 && value != 1) return MIXGRPO_EINVAL;
     const int old = g_use_pdl;
