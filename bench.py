@@ -141,6 +141,10 @@ class Workload:
         self.side = [torch.cuda.Stream(device=dev) for _ in range(WINDOW)]
         world = dist.get_world_size() if dist.is_initialized() else 1
         self.gbuf = torch.empty(world * N_MODELS, B, device=dev)      # all-gathered rewards, rank-major rows
+        self.px = None                                                # mixgrpo_b200.peer.PeerExchange (--collectives peer, N > 1)
+        self.gathered = None
+        self.prev_rows = torch.zeros(WINDOW, B, 4, device=dev)       # the other stats buffer (reduced one step late, off the critical path)
+        self.px_stream = torch.cuda.Stream(device=dev)
 
     def noises(self, window):
         nz = [None] * N_STEPS
@@ -162,16 +166,28 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
         with torch.cuda.stream(comm):
             dist.all_gather_into_tensor(w.gbuf, w.rewards)
             dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)
+    rew = rewards if rewards is not None else w.rewards
+    adv = None
+    if w.px is not None:
+        # The path's single exchange AND the advantages as ONE kernel over NVLink peer memory, plus the PREVIOUS step's
+        # logging sums as one all-reduce kernel (csrc/peer_kernels.cu) — on a side branch concurrent with the rollout,
+        # joined before the policy updates need the advantages.  No NCCL anywhere in the step.
+        w.px_stream.wait_stream(cur0)
+        with torch.cuda.stream(w.px_stream):
+            adv, w.gathered = w.px.gather_advantages(rew, B, w.weights)
+            w.px.allreduce_stats(w.prev_rows.view(-1))
     det = R.window_mask(N_STEPS, window)
     nz = [None] * N_STEPS
     for j, i in enumerate(window):
         nz[i] = (eps if eps is not None else w.eps)[j]
     _, _, traj, logps, _ = R.rollout(lambda lat, s, i: v_list[i], w.z0, w.sig, det, w.cfg, noises=nz)
-    rew = rewards if rewards is not None else w.rewards
-    if collectives and dist.is_initialized() and dist.get_world_size() > 1:
-        gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
-        _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
-    adv = grpo.compute_group_advantages(rew, B, w.weights)
+    if w.px is not None:
+        cur0.wait_stream(w.px_stream)
+    else:
+        if collectives and dist.is_initialized() and dist.get_world_size() > 1:
+            gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
+            _ = gathered                                                    # feeds logging only in parity mode (TR:427-437)
+        adv = grpo.compute_group_advantages(rew, B, w.weights)
     if comm is not None:
         cur0.wait_stream(comm)
     # the window's policy updates are independent of one another (TR:536-585 loops over them): one stream each, so
@@ -188,7 +204,7 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
     if parallel:
         for j in range(len(window)):
             cur.wait_stream(w.side[j])
-    if collectives:
+    if w.px is None and collectives:
         grpo.reduce_step_stats(w.stats_rows, group)
     return w.stats_rows, logps, grads
 
@@ -402,12 +418,28 @@ def run_native(args):
     # launch per step at any N; if NCCL capture is unavailable they run eagerly on a side stream instead.
     main_stream = torch.cuda.current_stream(dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    peer_mode = world > 1 and args.collectives == "peer"
+    if peer_mode:
+        from mixgrpo_b200.peer import PeerExchange
+        try:
+            w.px = PeerExchange()
+            failed = 0
+        except Exception as e:  # noqa: BLE001  (CUDA IPC unavailable on this box: every rank falls back together)
+            print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL on a side stream", file=sys.stderr)
+            failed = 1
+        t = torch.tensor([failed], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if int(t.item()):
+            if w.px is not None:
+                w.px.close()
+            w.px, peer_mode = None, False
     graph, (stats, logps, _), coll_in_graph = capture_step(w, window, comm_stream if args.collectives == "graph" else None)
+    coll_in_graph = coll_in_graph or peer_mode
     # eager mode: two graphs with their own stats rows, used alternately, so step k+1 never has to wait for step k's
     # all-reduce to finish reading its rows — the collectives overlap the next step completely
     graphs, rows = [graph], [w.stats_rows]
-    if world > 1 and not coll_in_graph:
-        w.stats_rows = torch.zeros_like(w.stats_rows)
+    if world > 1 and (peer_mode or not coll_in_graph):
+        w.stats_rows, w.prev_rows = w.prev_rows, w.stats_rows
         g2, _, _ = capture_step(w, window, None)
         graphs.append(g2)
         rows.append(w.stats_rows)
@@ -441,7 +473,9 @@ def run_native(args):
         for _ in range(args.steps):
             step()
         if world > 1:
-            if coll_in_graph:
+            if peer_mode:
+                w.px.allreduce_stats(rows[(counter[0] - 1) % len(graphs)].view(-1))   # the last step's sums (earlier ones were reduced one step late)
+            elif coll_in_graph:
                 dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)   # the last step's stats (earlier ones were reduced one step late)
             else:
                 main_stream.wait_stream(comm_stream)  # the last step's collectives end inside the timed region
@@ -487,13 +521,13 @@ def run_native(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
                                    "one prompt group per GPU", "io_dtypes": "model_output/noise bf16 in, latents/trajectory/log-prob fp32, grad bf16; arithmetic fp32", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
-                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
+                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "fused peer-memory kernels inside the step graph, no NCCL: reward gather + advantages (1 launch, st.global over NVLink + flags), [4x12x4] stats all-reduce (1 launch)" if peer_mode else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
                        "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages + rollout.policy_update (eager launches)"},
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches": (LAUNCHES_PER_STEP + (1 if peer_mode else 0)) * args.steps,
             "clocks": clk.summary(), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "check": {"loss": loss_host, "e2e_loss": e2e_loss, "logp_mean": float(logps[:, window[0]].mean().item())},
             "library": mixgrpo_b200.library_path(),
@@ -582,7 +616,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--collectives", default="eager", choices=["graph", "eager"], help="N>1: capture the two NCCL collectives in the step graph, or issue them eagerly on a side stream")
+    ap.add_argument("--collectives", default="peer", choices=["peer", "graph", "eager"],
+                    help="N>1: 'peer' = fused peer-memory kernels in the step graph (no NCCL); 'graph' = the two NCCL collectives captured in the step graph; 'eager' = NCCL on a side stream")
     ap.add_argument("--skip-e2e", action="store_true", help="(tuning only) skip the e2e and roofline legs")
     ap.add_argument("--profile-only", action="store_true", help="setup + warm-up + K timed steps between cudaProfilerStart/Stop, then exit (for ncu)")
     args = ap.parse_args()

@@ -218,7 +218,7 @@ int mixgrpo_grpo_loss(const float* new_logp, const float* old_logp, const float*
  *                                   rewards into every peer's region with st.global over NVLink, publishes a
  *                                   sequence flag (st.release.sys), waits for the peers' flags (ld.acquire.sys) and
  *                                   computes its advantages from the gathered matrix in the same CTA.
- *   mixgrpo_peer_allreduce          replaces the all_reduce(AVG)+.item() pairs of TR:586-600 for <= 64 floats:
+ *   mixgrpo_peer_allreduce          replaces the all_reduce(AVG)+.item() pairs of TR:586-600 for <= 256 floats:
  *                                   contributions are summed in rank order, so every rank gets the same bits.
  * A "region" is mixgrpo_peer_region_bytes(world, cap_floats) bytes of cudaMalloc'ed memory per rank
  * (cap_floats >= n_models*local_B), created with _alloc (which also returns a 64-byte CUDA IPC handle to ship to
@@ -254,7 +254,7 @@ int mixgrpo_peer_gather_advantages(void* const* regions_host, int rank, int worl
                                    const float* rewards, const float* weights, int n_models, int64_t local_B,
                                    int num_generations, int trim_size, int mode, float* gathered_out,
                                    float* advantages, void* stream);
-/*   values [count <= 64] fp32, reduced in place: sum over ranks (in rank order), divided by world when average != 0 */
+/*   values [count <= 256] fp32, reduced in place: sum over ranks (in rank order), divided by world when average != 0 */
 int mixgrpo_peer_allreduce(void* const* regions_host, int rank, int world, int64_t cap_floats, float* values,
                            int count, int average, void* stream);
 

@@ -4,65 +4,59 @@
 //   all-reduce(AVG) of the (loss, policy, kl, clip_frac) logging sums (TR:586-600)        -> ONE launch
 //
 // TR = /root/reference/fastvideo/train_grpo_flux.py.  The messages are tens to hundreds of bytes, i.e. pure latency:
-// a NCCL all_gather (launch + LL protocol, ~10-20 us) followed by a separate advantage kernel is replaced by one
+// a NCCL all_gather (launch + protocol, ~10-20 us) followed by a separate advantage kernel is replaced by one
 // single-CTA kernel that
-//   1. PUSHES this rank's rewards straight into every peer's "region" with st.global over NVLink/NVSwitch
-//      (the regions are cudaMalloc'ed once per rank and mapped into every peer with CUDA IPC),
-//   2. publishes a sequence number with st.release.sys into each peer's flag word,
-//   3. spins (ld.acquire.sys, bounded by a timeout) on its OWN flag words until every peer's push has landed,
-//   4. computes the advantages from shared memory with exactly the arithmetic of mg::group_adv_kernel.
-// No host involvement, no NCCL, no extra launch; the call counter lives in the region, so the kernel is CUDA-graph
-// capturable (pointers and arguments never change between replays).  Two parity-alternating buffers make back-to-back
-// calls safe without a second handshake: a rank can only reach call k+2 after it has seen every peer's flag of call
-// k+1, which a peer publishes after its call-k kernel (the last reader of buffer k&1) has completed.
+//   1. PUSHES this rank's rewards straight into every peer's "region" over NVLink/NVSwitch (the regions are
+//      cudaMalloc'ed once per rank and mapped into every peer with CUDA IPC).  Every float travels as ONE 64-bit word
+//      { call number : 32 | float bits : 32 } written with a single st.relaxed.sys.u64 — a scalar 64-bit store is
+//      atomic, so value and "this is call s" arrive together: no flag, no fence, no second round trip (the idea of
+//      NCCL's LL protocol, applied to a one-shot exchange);
+//   2. polls (ld.relaxed.sys.u64, bounded by a timeout) its OWN region until every word carries this call's number;
+//   3. computes the advantages from shared memory with exactly the arithmetic of mg::group_adv_kernel.
+// One-way NVLink latency is the whole cost.  No host involvement, no NCCL, no extra launch; the call counter lives in
+// the region, so the kernel is CUDA-graph capturable (pointers and arguments never change between replays).  Two
+// parity-alternating buffers make back-to-back calls safe without a handshake: a rank can only reach call k+2 after
+// it has received every peer's words of call k+1, which a peer sends after its call-k kernel (the last reader of buffer
+// k&1) has completed; a word of call k-2 still sitting in the buffer carries the wrong number and is never mistaken.
 //
 // Region layout (per rank, identical on all ranks):
 //   [0,256)     header: u32 seq[2] (calls completed per channel), u32 status (1 = a wait timed out)
-//   [256,512)   flags : u32 [channel 2][parity 2][kMaxWorld]
-//   [512, ...)  channel 0 data: float [parity 2][world][cap]      (reward matrices, cap >= n_models*local_B)
-//   then        channel 1 data: float [parity 2][world][kRedCap]  (logging sums)
+//   [256, ...)  channel 0: u64 [parity 2][world][cap]      (reward matrices, cap >= n_models*local_B)
+//   then        channel 1: u64 [parity 2][world][kRedCap]  (logging sums)
 #include "common.cuh"
 
 namespace mg {
 
 constexpr int kMaxWorld = MIXGRPO_PEER_MAX_WORLD;
-constexpr int kRedCap = 64;
+constexpr int kRedCap = 256;
 constexpr int kPeerThreads = 256;
 constexpr int kPeerWarps = kPeerThreads / 32;
-constexpr long long kHdrBytes = 256, kFlagBytes = 256;
+constexpr long long kHdrBytes = 256;
 
 struct PeerArgs {
   char* region[kMaxWorld];      // region[p] = rank p's region as mapped in THIS process (own region at [rank])
   int rank, world;
-  long long cap;                // floats per rank in channel 0
+  long long cap;                // words per rank in channel 0
   unsigned long long timeout_ns;
 };
 
-__host__ __device__ inline long long round256(long long x) { return (x + 255) / 256 * 256; }
 __host__ __device__ inline long long ch_data_offset(int ch, int world, long long cap) {
-  return kHdrBytes + kFlagBytes + (ch == 0 ? 0 : round256(2ll * world * cap * (long long)sizeof(float)));
+  return kHdrBytes + (ch == 0 ? 0 : 2ll * world * cap * (long long)sizeof(unsigned long long));
 }
 __host__ inline long long region_bytes(int world, long long cap) {
-  return ch_data_offset(1, world, cap) + 2ll * world * kRedCap * (long long)sizeof(float);
+  return ch_data_offset(1, world, cap) + 2ll * world * kRedCap * (long long)sizeof(unsigned long long);
 }
 
-__device__ __forceinline__ uint32_t* flag_ptr(char* region, int ch, int par, int p) {
-  return reinterpret_cast<uint32_t*>(region + kHdrBytes) + ((ch * 2 + par) * kMaxWorld + p);
-}
-__device__ __forceinline__ float* data_ptr(char* region, int ch, int par, int p, int world, long long cap) {
+__device__ __forceinline__ unsigned long long* word_ptr(char* region, int ch, int par, int p, int world, long long cap) {
   const long long slot = ch == 0 ? cap : kRedCap;
-  return reinterpret_cast<float*>(region + ch_data_offset(ch, world, cap)) + ((long long)par * world + p) * slot;
+  return reinterpret_cast<unsigned long long*>(region + ch_data_offset(ch, world, cap)) + ((long long)par * world + p) * slot;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void st_relaxed_sys(float* p, float v) { asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -71,51 +65,52 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Push `count` floats from src into slot [rank] of every rank's channel buffer, publish, and wait until every rank's
-// push into OUR region has landed.  Returns the buffer parity to read from (all threads); *ok is false after a timeout.
-// Must be called by all kPeerThreads threads.  s_bcast: two shared words.
-__device__ __forceinline__ int peer_exchange(const PeerArgs& a, int ch, const float* src, int count, uint32_t* s_bcast, bool* ok) {
-  char* mine = a.region[a.rank];
-  uint32_t* hdr = reinterpret_cast<uint32_t*>(mine);
+struct PeerCall {
+  uint32_t seq;     // this call's number (calls completed + 1)
+  int par;          // buffer parity
+};
+
+// Start a call: read the call counter and push `count` floats from src into slot [rank] of every rank's buffer.
+// All kPeerThreads threads.  s_bcast: two shared words ([1] is the "no timeout so far" flag).
+__device__ __forceinline__ PeerCall peer_push(const PeerArgs& a, int ch, const float* src, int count, uint32_t* s_bcast) {
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(a.region[a.rank]);
   if (threadIdx.x == 0) { s_bcast[0] = *reinterpret_cast<volatile uint32_t*>(hdr + ch) + 1u; s_bcast[1] = 1u; }
   __syncthreads();
-  const uint32_t s = s_bcast[0];
-  const int par = (int)(s & 1u);
+  PeerCall c;
+  c.seq = s_bcast[0];
+  c.par = (int)(c.seq & 1u);
   for (int i = threadIdx.x; i < count; i += kPeerThreads) {
-    const float val = src[i];
-    for (int q = 0; q < a.world; ++q) {
-      const int p = (a.rank + q) % a.world;                       // start with ourselves, spread the links
-      st_relaxed_sys(data_ptr(a.region[p], ch, par, a.rank, a.world, a.cap) + i, val);
+    const unsigned long long w = ((unsigned long long)c.seq << 32) | (unsigned long long)__float_as_uint(src[i]);
+    for (int q = 1; q <= a.world; ++q) {
+      const int p = (a.rank + q) % a.world;                       // peers first (their latency is the longer one), ourselves last
+      st_relaxed_sys(word_ptr(a.region[p], ch, c.par, a.rank, a.world, a.cap) + i, w);
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < a.world) {
-    const int p = threadIdx.x;
-    __threadfence_system();
-    st_release_sys(flag_ptr(a.region[p], ch, par, a.rank), s);     // "rank a.rank's data of call s is in your buffer"
-    const uint32_t* f = flag_ptr(mine, ch, par, p);
+  return c;
+}
+
+// Wait for word i of rank q's slot in OUR region to carry this call's number and return its float; NaN after a timeout.
+__device__ __forceinline__ float peer_poll(const PeerArgs& a, int ch, const PeerCall& c, int q, int i, uint32_t* s_bcast) {
+  const unsigned long long* wp = word_ptr(a.region[a.rank], ch, c.par, q, a.world, a.cap) + i;
+  unsigned long long w = ld_relaxed_sys(wp);
+  if ((uint32_t)(w >> 32) != c.seq) {
     const unsigned long long t0 = global_ns();
     unsigned spins = 0;
-    while (ld_acquire_sys(f) != s) {
-      if ((++spins & 0x3ffu) == 0 && a.timeout_ns && global_ns() - t0 > a.timeout_ns) {
-        s_bcast[1] = 0u;
-        *reinterpret_cast<volatile uint32_t*>(hdr + 2) = 1u;      // status: a wait timed out
-        break;
+    while ((uint32_t)((w = ld_relaxed_sys(wp)) >> 32) != c.seq) {
+      if ((++spins & 0xffu) == 0 && (*reinterpret_cast<volatile uint32_t*>(s_bcast + 1) == 0u ||
+                                    (a.timeout_ns && global_ns() - t0 > a.timeout_ns))) {
+        *reinterpret_cast<volatile uint32_t*>(s_bcast + 1) = 0u;  // tell the other pollers of this CTA to give up too
+        reinterpret_cast<volatile uint32_t*>(a.region[a.rank])[2] = 1u;   // status: a wait timed out
+        return __int_as_float(0x7fc00000);
       }
     }
   }
-  __syncthreads();
-  *ok = s_bcast[1] != 0u;
-  return par;
+  return __uint_as_float((uint32_t)w);
 }
 
-__device__ __forceinline__ void peer_commit(const PeerArgs& a, int ch) {   // after the last read of the buffers
+__device__ __forceinline__ void peer_commit(const PeerArgs& a, int ch, const PeerCall& c) {   // after the last poll
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t* hdr = reinterpret_cast<uint32_t*>(a.region[a.rank]);
-    *reinterpret_cast<volatile uint32_t*>(hdr + ch) = *reinterpret_cast<volatile uint32_t*>(hdr + ch) + 1u;
-  }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(a.region[a.rank]) + ch) = c.seq;
 }
 
 // ------------------------------------------------------------------ gather + advantages
@@ -173,17 +168,22 @@ __global__ void __launch_bounds__(kPeerThreads) peer_gather_adv_kernel(const __g
   float* s_g = s_dyn;                         // [M][NB] gathered rewards, columns rank-major
   float* s_stat = s_dyn + (size_t)M * NB;     // [groups][M][2]
 
-  bool ok;
-  const int par = peer_exchange(p.peer, 0, p.rewards, count, s_bcast, &ok);
-  char* mine = p.peer.region[p.peer.rank];
+  const PeerCall call = peer_push(p.peer, 0, p.rewards, count, s_bcast);
   for (int idx = tid; idx < W * count; idx += kPeerThreads) {
     const int q = idx / count, r = idx - q * count, m = r / LB, b = r - m * LB;
-    const float val = ok ? ld_relaxed_sys(data_ptr(mine, 0, par, q, W, p.peer.cap) + r) : __int_as_float(0x7fc00000);
+    const float val = peer_poll(p.peer, 0, call, q, r, s_bcast);
     s_g[(size_t)m * NB + q * LB + b] = val;
     if (p.gathered_out) p.gathered_out[(size_t)m * NB + q * LB + b] = val;
   }
   for (int b = tid; b < LB; b += kPeerThreads) p.adv_out[b] = 0.f;   // ragged tails stay zero like the reference (TR:445)
   __syncthreads();
+  if (s_bcast[1] == 0u) {                                            // a peer never showed up: poison every output
+    const float nan = __int_as_float(0x7fc00000);
+    for (int b = tid; b < LB; b += kPeerThreads) p.adv_out[b] = nan;
+    if (p.gathered_out) for (int i = tid; i < M * NB; i += kPeerThreads) p.gathered_out[i] = nan;
+    peer_commit(p.peer, 0, call);
+    return;
+  }
 
   const int lo = p.peer.rank * LB, hi = lo + LB;                     // this rank's columns
   if (p.mode == MIXGRPO_ADV_GLOBAL) {                                // TR:498: statistics of the gathered vector
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_gather_adv_kernel(const __g
       p.adv_out[j - lo] = out;
     }
   }
-  peer_commit(p.peer, 0);
+  peer_commit(p.peer, 0, call);
 }
 
 // ------------------------------------------------------------------ small all-reduce (sum in rank order / average)
@@ -231,18 +231,18 @@ struct ReduceParams {
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __grid_constant__ ReduceParams p) {
   pdl_prologue();
   __shared__ uint32_t s_bcast[2];
-  bool ok;
-  const int par = peer_exchange(p.peer, 1, p.vals, p.count, s_bcast, &ok);
-  char* mine = p.peer.region[p.peer.rank];
+  const PeerCall call = peer_push(p.peer, 1, p.vals, p.count, s_bcast);
   const int W = p.peer.world;
   if ((int)threadIdx.x < p.count) {
     // every rank adds the W contributions in rank order: the result is bit-identical on all ranks and run to run
-    float acc = ld_relaxed_sys(data_ptr(mine, 1, par, 0, W, p.peer.cap) + threadIdx.x);
-    for (int q = 1; q < W; ++q) acc = __fadd_rn(acc, ld_relaxed_sys(data_ptr(mine, 1, par, q, W, p.peer.cap) + threadIdx.x));
+    float acc = peer_poll(p.peer, 1, call, 0, threadIdx.x, s_bcast);
+    for (int q = 1; q < W; ++q) acc = __fadd_rn(acc, peer_poll(p.peer, 1, call, q, threadIdx.x, s_bcast));
     if (p.average) acc = __fdiv_rn(acc, (float)W);
-    p.vals[threadIdx.x] = ok ? acc : __int_as_float(0x7fc00000);
+    p.vals[threadIdx.x] = acc;
   }
-  peer_commit(p.peer, 1);
+  __syncthreads();
+  if (s_bcast[1] == 0u && (int)threadIdx.x < p.count) p.vals[threadIdx.x] = __int_as_float(0x7fc00000);   // timed out
+  peer_commit(p.peer, 1, call);
 }
 
 static unsigned long long g_peer_timeout_ms = 30000ull;   // mixgrpo_set_tuning key 2 (0 = wait forever)

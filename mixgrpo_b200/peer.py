@@ -58,24 +58,42 @@ class PeerExchange:
                 raise ValueError(f"mixgrpo_b200: PeerExchange supports up to {PEER_MAX_WORLD} ranks of one node")
             handle = (C.c_ubyte * PEER_HANDLE_BYTES)()
             region = C.c_void_p()
+            err: Optional[str] = None
             with torch.cuda.device(self.device):
-                _cabi.check(self._lib.mixgrpo_peer_region_alloc(self.world, self.cap, C.byref(region), handle), "peer_region_alloc")
+                rc = self._lib.mixgrpo_peer_region_alloc(self.world, self.cap, C.byref(region), handle)
+            if rc != 0:
+                err = f"rank {self.rank}: peer_region_alloc failed with code {rc}"
+                if self.world == 1:
+                    raise RuntimeError("mixgrpo_b200: " + err)
             self._owned = region.value
             self._ptrs = [0] * self.world
             self._ptrs[self.rank] = region.value
             if self.world > 1:
+                # every step below is collective and every rank reaches every step, whatever failed locally: a rank that
+                # cannot allocate or map reports it, and ALL ranks raise together instead of deadlocking in a barrier
                 handles: List[Optional[bytes]] = [None] * self.world
-                dist.all_gather_object(handles, bytes(handle), group=group)
-                with torch.cuda.device(self.device):
-                    for q, hb in enumerate(handles):
-                        if q == self.rank:
-                            continue
-                        buf = (C.c_ubyte * PEER_HANDLE_BYTES).from_buffer_copy(hb)
-                        peer = C.c_void_p()
-                        _cabi.check(self._lib.mixgrpo_peer_region_open(buf, C.byref(peer)), f"peer_region_open(rank {q})")
-                        self._opened.append(peer.value)
-                        self._ptrs[q] = peer.value
-                dist.barrier(group=group)             # every region is mapped everywhere before the first push
+                dist.all_gather_object(handles, None if err else bytes(handle), group=group)
+                if err is None and all(h is not None for h in handles):
+                    with torch.cuda.device(self.device):
+                        for q, hb in enumerate(handles):
+                            if q == self.rank:
+                                continue
+                            buf = (C.c_ubyte * PEER_HANDLE_BYTES).from_buffer_copy(hb)
+                            peer = C.c_void_p()
+                            rc = self._lib.mixgrpo_peer_region_open(buf, C.byref(peer))
+                            if rc != 0:
+                                err = f"rank {self.rank}: peer_region_open(rank {q}) failed with code {rc} ({self._lib.mixgrpo_error_string(rc).decode()})"
+                                break
+                            self._opened.append(peer.value)
+                            self._ptrs[q] = peer.value
+                elif err is None:
+                    err = f"rank {self.rank}: a peer could not allocate its region"
+                errs: List[Optional[str]] = [None] * self.world
+                dist.all_gather_object(errs, err, group=group)    # also the "everything is mapped everywhere" rendezvous
+                if any(errs):
+                    self._distributed = True
+                    self.close()
+                    raise RuntimeError("mixgrpo_b200: PeerExchange setup failed: " + "; ".join(e for e in errs if e))
                 self._distributed = True
         self._regions_c = (C.c_void_p * self.world)(*self._ptrs)
 
@@ -151,12 +169,12 @@ class PeerExchange:
         return adv, gathered
 
     def allreduce_stats(self, values: torch.Tensor, average: bool = True) -> torch.Tensor:
-        """In-place sum (in rank order — same bits on every rank) or average of ``values`` (fp32, <= 64 entries) over
+        """In-place sum (in rank order — same bits on every rank) or average of ``values`` (fp32, <= 256 entries) over
         the ranks: the ONE reduction per ``train_one_step`` that replaces TR:586-600's four all-reduce + ``.item()``
         pairs per (sample, window step)."""
         _ops._require_cuda(values, "values")
-        if values.dtype != torch.float32 or not values.is_contiguous() or values.numel() < 1 or values.numel() > 64:
-            raise ValueError("mixgrpo_b200: allreduce_stats takes a contiguous fp32 tensor of 1..64 entries")
+        if values.dtype != torch.float32 or not values.is_contiguous() or values.numel() < 1 or values.numel() > 256:
+            raise ValueError("mixgrpo_b200: allreduce_stats takes a contiguous fp32 tensor of 1..256 entries")
         with torch.cuda.device(values.device):
             rc = self._lib.mixgrpo_peer_allreduce(self._regions_c, self.rank, self.world, self.cap, values.data_ptr(), values.numel(),
                                                   1 if average else 0, _ops._stream_ptr(values.device))

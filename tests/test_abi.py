@@ -65,6 +65,20 @@ def test_host_side_argument_validation_needs_no_gpu():
     assert lib.mixgrpo_grpo_loss(None, None, None, 1, 1e-4, 5.0, 0.0, 12.0, None, None, None, None) == -1
     assert lib.mixgrpo_pack_latents(None, None, 0, 1, 16, 8, 8, None) == -1
     assert lib.mixgrpo_set_tuning(99, 1) == -1
+    # peer exchange: region sizing is pure host arithmetic; bad ranks / worlds / capacities never reach CUDA
+    assert lib.mixgrpo_peer_region_bytes(8, 4096) == 256 + 2 * 8 * 4096 * 8 + 2 * 8 * 256 * 8
+    assert lib.mixgrpo_peer_region_bytes(17, 16) == 0 and lib.mixgrpo_peer_region_bytes(0, 16) == 0
+    regs = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.mixgrpo_peer_gather_advantages(None, 0, 2, 64, 1, None, 1, 4, 4, 0, 0, None, 1, None) == -1
+    assert lib.mixgrpo_peer_gather_advantages(regs, 2, 2, 64, 1, None, 1, 4, 4, 0, 0, None, 1, None) == -1       # rank >= world
+    assert lib.mixgrpo_peer_gather_advantages(regs, 0, 2, 64, 1, None, 3, 4, 4, 0, 0, None, 1, None) == -1       # 3 models, no weights
+    assert lib.mixgrpo_peer_gather_advantages(regs, 0, 2, 8, 1, 1, 3, 4, 4, 0, 0, None, 1, None) == -3           # 12 floats > cap 8
+    assert lib.mixgrpo_peer_gather_advantages(regs, 0, 2, 64, 1, None, 1, 4, 4, 0, 7, None, 1, None) == -1       # bad mode
+    assert lib.mixgrpo_peer_allreduce(regs, 0, 2, 64, 1, 257, 1, None) == -3
+    assert lib.mixgrpo_peer_allreduce(regs, 0, 2, 64, None, 4, 1, None) == -1
+    assert lib.mixgrpo_peer_region_open(None, None) == -1
+    old = lib.mixgrpo_set_tuning(2, 1234)
+    assert lib.mixgrpo_set_tuning(2, old) == 1234
 
 
 def test_python_layer_refuses_cpu_tensors():
@@ -82,6 +96,9 @@ def test_python_layer_refuses_cpu_tensors():
         grpo.grpo_loss(torch.zeros(2), torch.zeros(2), torch.zeros(2), 1e-4, 5.0, 0.0, 1, 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.pack_latents(torch.zeros(1, 16, 4, 4), 1, 16, 4, 4)
+    from mixgrpo_b200.peer import PeerExchange
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PeerExchange(device=torch.device("cpu"))
 
 
 def test_product_never_imports_oracle():

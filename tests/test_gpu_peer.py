@@ -154,7 +154,7 @@ def test_allreduce_rank_order_sum_is_bitwise_reproducible(world, short_timeout):
     eps = PeerExchange.local_ranks(world, dev)
     try:
         g = torch.Generator().manual_seed(5)
-        for call, (count, avg) in enumerate([(4, True), (4, False), (64, True), (1, True)]):
+        for call, (count, avg) in enumerate([(4, True), (4, False), (256, True), (1, True)]):
             vals = [torch.randn(count, generator=g) * 10 ** (r % 3) for r in range(world)]
             want = vals[0].clone()
             for q in range(1, world):
@@ -167,7 +167,7 @@ def test_allreduce_rank_order_sum_is_bitwise_reproducible(world, short_timeout):
             for out in res:
                 assert torch.equal(out.cpu(), want), call
         with pytest.raises(ValueError):
-            eps[0].allreduce_stats(torch.zeros(65, device=dev))
+            eps[0].allreduce_stats(torch.zeros(257, device=dev))
     finally:
         for e in eps:
             e.close()
