@@ -143,6 +143,7 @@ class Workload:
         self.gbuf = torch.empty(world * N_MODELS, B, device=dev)      # all-gathered rewards, rank-major rows
         self.px = None                                                # mixgrpo_b200.peer.PeerExchange (--collectives peer, N > 1)
         self.gathered = None
+        self.single_pass = False                                      # --policy single: mixgrpo_policy_step (one launch, 12 B/elem)
         self.prev_rows = torch.zeros(WINDOW, B, 4, device=dev)       # the other stats buffer (reduced one step late, off the critical path)
         self.px_stream = torch.cuda.Stream(device=dev)
 
@@ -200,7 +201,8 @@ def native_step(w: Workload, window, v_list=None, eps=None, rewards=None, group=
         with torch.cuda.stream(s):
             _, _, grads[j] = R.policy_update(v_list[t], traj[:, t], traj[:, t + 1], logps[:, t], adv, w.sig, t, w.cfg, clip_range=CLIP,
                                              adv_clip_max=ADV_CLIP, kl_coeff=KL, gradient_accumulation_steps=GA,
-                                             num_train_timesteps=len(window), stats_rows=w.stats_rows[j], accumulate=False)
+                                             num_train_timesteps=len(window), stats_rows=w.stats_rows[j], accumulate=False,
+                                             single_pass=w.single_pass)
     if parallel:
         for j in range(len(window)):
             cur.wait_stream(w.side[j])
@@ -409,6 +411,7 @@ def run_native(args):
     mixgrpo_b200.load_library()
     peak, peak_kind = load_peaks()
     w = Workload(dev, rank)
+    w.single_pass = args.policy == "single"
     states = GRPOTrainingStates(iters_per_group=25, group_size=WINDOW, max_timesteps=N_STEPS - 2, prog_overlap=True, prog_overlap_step=1)
     window = states.get_current_timesteps()
 
@@ -503,7 +506,7 @@ def run_native(args):
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"tuning_only": True, "n_gpus": world, "ms_per_step": ms_per_step, "value": value, "collectives": args.collectives,
-                              "in_graph": coll_in_graph}), flush=True)
+                              "in_graph": coll_in_graph, "policy": args.policy}), flush=True)
         if world > 1:
             torch.cuda.synchronize(dev); dist.barrier(); os._exit(0)
         return
@@ -618,6 +621,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collectives", default="peer", choices=["peer", "graph", "eager"],
                     help="N>1: 'peer' = fused peer-memory kernels in the step graph (no NCCL); 'graph' = the two NCCL collectives captured in the step graph; 'eager' = NCCL on a side stream")
+    ap.add_argument("--policy", default="pair", choices=["pair", "single"],
+                    help="policy update as two launches (log-prob+loss forward, backward: 22 B/elem) or the single-pass kernel (12 B/elem)")
     ap.add_argument("--skip-e2e", action="store_true", help="(tuning only) skip the e2e and roofline legs")
     ap.add_argument("--profile-only", action="store_true", help="setup + warm-up + K timed steps between cudaProfilerStart/Stop, then exit (for ncu)")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MIXGRPO_ABI_VERSION 2
+#define MIXGRPO_ABI_VERSION 3
 
 /* element type of model_output / noise / grad_model_output */
 enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
@@ -61,6 +61,7 @@ typedef struct mixgrpo_philox_args {
 #define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
 #define MIXGRPO_EALIGN   (-2)  /* reserved */
 #define MIXGRPO_ENOSPACE (-3)  /* workspace too small */
+#define MIXGRPO_EUNSUPPORTED (-4) /* this entry point does not cover the shape (see mixgrpo_policy_step); nothing was launched */
 
 /* Per-step scalar block.  All values are fp32 numbers computed on the HOST with the reference's
  * operator order (mixgrpo_b200/coefs.py); where torch would cast a 0-dim scalar to bf16 before a
@@ -94,17 +95,19 @@ typedef struct mixgrpo_step_coefs {
   float c[16];
 } mixgrpo_step_coefs;
 
-/* Bytes of zero-initialised device workspace the step kernels need for (B, n): one 64-bit packed
- * accumulator per sample ([fixed-point sum | poison | arrival count], csrc/step_kernels.cu) for the
- * deterministic log-prob reduction.  Kernels leave the words zeroed again, so one allocation can be
- * reused by successive launches on the same stream. */
+/* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 16-byte record per
+ * sample — a 64-bit packed accumulator ([fixed-point sum | poison | arrival count], csrc/step_kernels.cu) for the
+ * deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu).  The layout does
+ * not depend on B and kernels leave the accumulators zeroed again, so one allocation can be reused by successive
+ * launches of any batch size on the same stream (never by launches that may run concurrently). */
 int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
 
 /* ABI / build introspection. */
 int mixgrpo_abi_version(void);
 const char* mixgrpo_build_info(void);          /* e.g. "sm_100a nvcc 12.9 ..." (static string) */
-int mixgrpo_set_tuning(int key, int value);    /* knobs (0: max CTAs/sample, 1: PDL on/off, 2: peer-wait timeout in ms, 0 = forever);
-                                                  returns the previous value or <0 */
+int mixgrpo_set_tuning(int key, int value);    /* knobs (0: max CTAs/sample, 1: PDL on/off, 2: peer-wait timeout in ms, 0 = forever,
+                                                  3: single-pass policy kernel CTAs/SM, 4: its cooperative launch on/off, 5: its wait
+                                                  timeout in ms); returns the previous value or <0 */
 const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGetErrorString for >0) */
 
 /* ---- fused sampler step + Gaussian transition log-prob ---------------------------------------
@@ -184,6 +187,20 @@ int mixgrpo_policy_bwd(int family, const void* v, int v_dtype, const float* x, i
                        const float* x_next, int64_t in_bs, const float* new_logp,
                        const mixgrpo_loss_args* loss, void* grad_v, int64_t B, int64_t n,
                        const mixgrpo_step_coefs* coefs_host, unsigned flags, void* stream);
+
+/* ---- single-pass policy update: log-prob forward + loss + log-prob backward in ONE launch, 12 B/elem ----------
+ * Same inputs, outputs and bits as mixgrpo_policy_fwd followed by mixgrpo_policy_bwd (new log-probs [B], stats rows,
+ * grad_v), but v / x / x_next are read ONCE: a persistent, co-resident (cooperatively launched) grid keeps the
+ * residuals x_next - mean in shared memory while the per-sample sums complete, then turns them into grad_v
+ * (csrc/policy_kernels.cu).  Returns MIXGRPO_EUNSUPPORTED — nothing launched — when the residuals do not fit on
+ * chip (more than ~27 tiles of 2048 scalars per SM, i.e. B*n > ~8 M), for ragged / unaligned tensors (n % 8, strides,
+ * 32-byte alignment); call the two-launch pair then.  workspace as for the step kernels; it must not be shared with
+ * a launch that can run concurrently.  A wait longer than the timeout (mixgrpo_set_tuning key 5, default 10 s) sets
+ * the workspace's status word and yields NaN gradients instead of hanging the GPU. */
+int mixgrpo_policy_step(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                        const float* x_next, int64_t in_bs, float* logp_out, void* grad_v, void* workspace,
+                        int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                        const mixgrpo_loss_args* loss, unsigned flags, void* stream);
 
 /* ---- reward -> group-relative advantage -------------------------------------------------------
  * Replaces TR:439-501.  rewards is [n_models, local_B] fp32 (one all-gathered or rank-local

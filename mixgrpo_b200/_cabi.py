@@ -16,8 +16,9 @@ SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC, SRC_PHILOX = 0, 1, 2, 3
 FLAG_ROUND_LIKE_TORCH = 1
 FLAG_PDL_EARLY_LOADS = 2
 ADV_GROUP_LOCAL, ADV_GROUP_SPLIT, ADV_GLOBAL = 0, 1, 2
+EUNSUPPORTED = -4
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class StepCoefs(C.Structure):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "mixgrpo_logprob_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _CP, _U, _P]),
     "mixgrpo_policy_fwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),
     "mixgrpo_policy_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _LP, _P, _I64, _I64, _CP, _U, _P]),
+    "mixgrpo_policy_step": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),
     "mixgrpo_cast_rows": (_I, [_P, _I, _P, _I64, _I64, _I64, _P]),
     "mixgrpo_group_advantages": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P, _I64, _P, _P]),
     "mixgrpo_grpo_loss": (_I, [_P, _P, _P, _I64, _D, _D, _D, _D, _P, _P, _P, _P]),

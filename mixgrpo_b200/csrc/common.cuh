@@ -127,6 +127,7 @@ __device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned lo
 extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_kernels.cu
 }  // namespace mg
 int mixgrpo_peer_set_timeout_ms(int ms);   // mixgrpo_set_tuning key 2, defined in peer_kernels.cu
+int mixgrpo_policy_set_tuning(int key, int value);   // keys 3-5, defined in policy_kernels.cu
 namespace mg {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

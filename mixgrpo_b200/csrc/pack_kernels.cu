@@ -117,6 +117,7 @@ extern "C" __attribute__((visibility("default"))) const char* mixgrpo_error_stri
     case MIXGRPO_EINVAL: return "mixgrpo: invalid argument";
     case MIXGRPO_EALIGN: return "mixgrpo: misaligned pointer";
     case MIXGRPO_ENOSPACE: return "mixgrpo: workspace too small";
+    case MIXGRPO_EUNSUPPORTED: return "mixgrpo: shape not covered by this entry point (nothing launched)";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "mixgrpo: unknown error";
   }
 }

@@ -16,11 +16,9 @@
 // log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> CTA -> ONE packed fixed-point atomicAdd per
 // CTA (count + sum in a 64-bit word): order-independent, hence bitwise reproducible; the last arriver
 // writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below.
-#include "common.cuh"
+#include "step_math.cuh"
 
 namespace mg {
-
-enum Family { kFlow = 0, kDance = 1, kDpm = 2 };
 
 struct StepParams {
   const void* v;
@@ -41,112 +39,6 @@ struct StepParams {
   LossParams loss;          // fused policy path (SRC_GIVEN only): old log-probs / advantages / stats rows, or nullptrs
 };
 
-// ------------------------------------------------------------------ per-tile arithmetic
-// FAM/SRC/ORDER/RND/SDE are compile-time so each instantiation is straight-line code.
-template <int FAM, int SRC, int ORDER, bool RND, bool SDE, int N>
-__device__ __forceinline__ void tile_math(const mixgrpo_step_coefs& k, const float (&v)[N], const float (&x)[N],
-                                           const float (&a)[N], const float (&m1)[N], const float (&m2)[N],
-                                           float (&xn)[N], float (&x0)[N], float (&mu)[N], float (&dd)[N]) {
-  const float* c = k.c;
-  float t[N];
-  // x0 = x - sigma*v          (SU:175, SU:226, SU:394)
-#pragma unroll
-  for (int i = 0; i < N; ++i) t[i] = __fmul_rn(c[0], v[i]);
-  round_like_torch<RND>(t);
-#pragma unroll
-  for (int i = 0; i < N; ++i) x0[i] = __fsub_rn(x[i], t[i]);
-
-  if constexpr (FAM == kFlow) {
-    // mean = x*c_x + (v*c_v)*dt   (SU:186)
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = __fmul_rn(v[i], c[2]);
-    round_like_torch<RND>(t);
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = __fmul_rn(t[i], c[3]);
-    round_like_torch<RND>(t);
-#pragma unroll
-    for (int i = 0; i < N; ++i) mu[i] = __fadd_rn(__fmul_rn(x[i], c[1]), t[i]);
-    if constexpr (SRC == MIXGRPO_SRC_NOISE) {            // SU:195
-#pragma unroll
-      for (int i = 0; i < N; ++i) t[i] = __fmul_rn(c[4], a[i]);
-      round_like_torch<RND>(t);
-#pragma unroll
-      for (int i = 0; i < N; ++i) xn[i] = __fadd_rn(mu[i], t[i]);
-    } else if constexpr (SRC == MIXGRPO_SRC_DETERMINISTIC) {   // SU:198-199
-#pragma unroll
-      for (int i = 0; i < N; ++i) t[i] = __fmul_rn(c[5], v[i]);
-      round_like_torch<RND>(t);
-#pragma unroll
-      for (int i = 0; i < N; ++i) xn[i] = __fadd_rn(x[i], t[i]);
-    }
-  } else if constexpr (FAM == kDance) {
-    // mean = x + dsigma*v       (SU:224)
-#pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = __fmul_rn(c[1], v[i]);
-    round_like_torch<RND>(t);
-#pragma unroll
-    for (int i = 0; i < N; ++i) mu[i] = __fadd_rn(x[i], t[i]);
-    if constexpr (SDE) {         // score / drift correction, SU:231-234
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        float s = __fdiv_rn(-__fsub_rn(x[i], __fmul_rn(x0[i], c[2])), c[3]);
-        mu[i] = __fadd_rn(mu[i], __fmul_rn(__fmul_rn(s, c[4]), c[5]));
-      }
-    }
-    if constexpr (SRC == MIXGRPO_SRC_NOISE) {            // SU:238
-#pragma unroll
-      for (int i = 0; i < N; ++i) xn[i] = __fadd_rn(mu[i], __fmul_rn(a[i], c[6]));
-    } else if constexpr (SRC == MIXGRPO_SRC_DETERMINISTIC) {   // SU:240
-#pragma unroll
-      for (int i = 0; i < N; ++i) xn[i] = mu[i];
-    }
-  } else {  // kDpm: data-prediction multistep, signs folded into the coefficients
-    float d1[N], d2[N];
-    if constexpr (ORDER == 2) {                          // SU:490
-#pragma unroll
-      for (int i = 0; i < N; ++i) d1[i] = __fmul_rn(c[1], __fsub_rn(x0[i], m1[i]));
-    } else if constexpr (ORDER == 3) {                   // SU:607-610
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        float d10 = __fmul_rn(c[1], __fsub_rn(x0[i], m1[i]));
-        float d11 = __fmul_rn(c[2], __fsub_rn(m1[i], m2[i]));
-        float dd = __fsub_rn(d10, d11);
-        d1[i] = __fadd_rn(d10, __fmul_rn(c[3], dd));
-        d2[i] = __fmul_rn(c[4], dd);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float m = __fadd_rn(__fmul_rn(c[5], x[i]), __fmul_rn(c[6], x0[i]));
-      if constexpr (ORDER >= 2) m = __fadd_rn(m, __fmul_rn(c[7], d1[i]));
-      if constexpr (ORDER == 3) m = __fadd_rn(m, __fmul_rn(c[8], d2[i]));
-      mu[i] = m;
-    }
-    if constexpr (SRC == MIXGRPO_SRC_NOISE) {            // SU:434, SU:510, SU:620
-#pragma unroll
-      for (int i = 0; i < N; ++i) xn[i] = __fadd_rn(mu[i], __fmul_rn(c[13], a[i]));
-    } else if constexpr (SRC == MIXGRPO_SRC_DETERMINISTIC) {   // SU:436, SU:516-526, SU:623-628
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        float o = __fadd_rn(__fmul_rn(c[9], x[i]), __fmul_rn(c[10], x0[i]));
-        if constexpr (ORDER >= 2) o = __fadd_rn(o, __fmul_rn(c[11], d1[i]));
-        if constexpr (ORDER == 3) o = __fadd_rn(o, __fmul_rn(c[12], d2[i]));
-        xn[i] = o;
-      }
-    }
-  }
-  if constexpr (SRC == MIXGRPO_SRC_GIVEN) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) xn[i] = a[i];
-  }
-  // squared residual of the transition (SU:202, SU:245, SU:377)
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const float d = __fsub_rn(xn[i], mu[i]);
-    dd[i] = d * d;
-  }
-}
-
 // ------------------------------------------------------------------ the streaming kernel
 // Grid (ctas_per_sample, B); CTA = 256 threads; a CTA-tile is 2048 consecutive scalars of one sample and
 // thread t owns scalars [8t, 8t+8) of it in every stream (one LDG.128 for bf16, one LDG.256 for fp32, one
@@ -164,9 +56,6 @@ __device__ __forceinline__ void tile_math(const mixgrpo_step_coefs& k, const flo
 //   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
 //   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2); a contribution that is not finite
 //   or would overflow the field (mean squared normalised residual > 510) poisons the sample -> NaN.
-constexpr int kTile = kThreads * kVec;          // scalars per CTA-tile
-constexpr int kCountBits = 12, kPoisonBits = 12;
-constexpr int kMaxCtasPerSample = (1 << kCountBits) - 1;
 
 template <class T, bool VECTOR>
 __device__ __forceinline__ void load_tile(const T* base, long long off, long long n, float (&r)[kVec]) {
@@ -281,7 +170,7 @@ step_kernel(const __grid_constant__ StepParams p) {
       r = 0.f;
     }
     add += __float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits);
-    const unsigned long long old = atomicAdd(&p.acc[b], add);
+    const unsigned long long old = atomicAdd(&p.acc[kWsStride * b], add);
     if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
       const unsigned long long tot = old + add;
       float q = (float)((double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0));
@@ -289,7 +178,7 @@ step_kernel(const __grid_constant__ StepParams p) {
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
       p.logp_out[b] = lp;
-      p.acc[b] = 0ull;
+      p.acc[kWsStride * b] = 0ull;
       if constexpr (SRC == MIXGRPO_SRC_GIVEN) {
         // fused policy path: the sample's clipped-ratio loss terms (TR:560-583, one sample = the reference's B == 1)
         // are added to its own stats row by this single thread — ordered across launches, no extra kernel
@@ -397,11 +286,14 @@ using namespace mg;
 
 extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n) {
   if (B <= 0 || n <= 0) return 0;
-  return ((B * (int64_t)sizeof(unsigned long long) + 255) / 256) * 256;   // one packed accumulator per sample
+  // one 16-byte record per sample: { packed 64-bit accumulator | 32-bit epoch | 32-bit status (record 0) } — the layout
+  // does not depend on B, so calls with different batch sizes can share one zero-initialised allocation
+  return ((B * (int64_t)(kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
 }
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
   if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
+  if (key >= 3 && key <= 5) return mixgrpo_policy_set_tuning(key, value);
   if (key == 1) {
     if (value != 0 && value != 1) return MIXGRPO_EINVAL;
     const int old = g_use_pdl;

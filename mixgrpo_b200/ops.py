@@ -295,6 +295,37 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     return grad_v
 
 
+def policy_step(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, coefs: StepCoefs, old_logp: torch.Tensor,
+                advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float, denom: float,
+                stats_rows: Optional[torch.Tensor] = None, round_like_torch: bool = False, accumulate: bool = True):
+    """Single-pass policy update (mixgrpo_policy_step): ``(new_log_probs [B], grad_model_output)`` in ONE launch that reads
+    v / x / x_next once (12 B/elem instead of 22).  Returns ``None`` — nothing launched — when the shape is not covered
+    (residuals do not fit on chip, ragged or unaligned tensors); the caller then uses ``policy_forward`` + ``policy_backward``."""
+    global launch_count
+    lib = _cabi.lib()
+    for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample")):
+        _require_cuda(t, nm)
+    vd = _dtype_code(v, "model_output")
+    v = v if v.is_contiguous() else v.contiguous()
+    B, n, dev = v.shape[0], v[0].numel(), v.device
+    x, x_bs = _rows(x.to(torch.float32), "latents")
+    x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
+    la, keep = _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, dev, accumulate)
+    logp = torch.empty((B,), dtype=torch.float32, device=dev)
+    grad_v = torch.empty_like(v)
+    ws = _workspace(dev, B, n)
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    with torch.cuda.device(dev):
+        rc = lib.mixgrpo_policy_step(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, logp.data_ptr(),
+                                     grad_v.data_ptr(), ws.data_ptr(), ws.numel(), B, n, C.byref(coefs), C.byref(la), flags, _stream_ptr(dev))
+    del keep
+    if rc == _cabi.EUNSUPPORTED:
+        return None
+    _cabi.check(rc, "policy_step")
+    launch_count += 1
+    return logp, grad_v
+
+
 def cast_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     """dst[b] = float32(src[b]) for a (B, ...) bf16|f32 contiguous ``src`` and an fp32 ``dst`` view whose per-sample
     block is contiguous (e.g. ``all_latents[:, 0]``): seeds the trajectory buffer (SU:26, SU:153)."""

@@ -180,12 +180,15 @@ def balance_pos_neg(samples: List[dict], use_random: bool = False, rng: Optional
 def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Tensor, old_log_probs: torch.Tensor,
                   advantages: torch.Tensor, sigmas: torch.Tensor, index: int, cfg: SamplerConfig, *, clip_range: float,
                   adv_clip_max: float, kl_coeff: float, gradient_accumulation_steps: int, num_train_timesteps: int,
-                  stats_rows: Optional[torch.Tensor] = None, accumulate: bool = True):
+                  stats_rows: Optional[torch.Tensor] = None, accumulate: bool = True, single_pass: bool = False):
     """One (samples, window step) policy update, TR:542-585 without autograd: given the model output ``v`` for
     the stored ``latents`` it returns ``(stats_rows, new_log_probs [B], grad_v)`` where ``grad_v`` is dloss/dv — hand it
     to ``v.backward(grad_v)`` to continue into the DiT.  ``stats_rows`` ([B,4] fp32, optional) accumulates each sample's
     (loss, policy_loss, kl_loss, clip_frac) (``accumulate=False`` overwrites instead); ``stats_rows.sum(0)`` is what
-    TR:588-600 adds up.  Two launches, no sync."""
+    TR:588-600 adds up.  Two launches, no sync.  ``single_pass=True`` uses mixgrpo_policy_step instead when the batch's
+    residuals fit on chip (up to ~8 M latent scalars, e.g. (24, 4096, 64)): ONE launch that reads every latent byte once
+    (12 instead of 22 B/elem from HBM, same bits).  It is opt-in because on B200 the pair is as fast or faster: the
+    backward's re-reads hit the 126 MB L2, while the single pass pays a grid-wide dependency (profiles/r01_policy_step.md)."""
     mode = _mode(cfg.rounding)
     bf16_v = v.dtype == torch.bfloat16
     rnd = bf16_v and mode != "fp32"
@@ -198,6 +201,11 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     # sum_i loss_i / (GA*T); the fused kernels do exactly that per sample: forward = log-prob + loss terms into the
     # sample's stats row, backward = dL/dlogp evaluated in place + closed-form chain.  Two launches, no loss kernel.
     denom = float(gradient_accumulation_steps * num_train_timesteps)
+    if single_pass:
+        res = _ops.policy_step(fam, vd, latents, next_latents, k, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff, denom,
+                               stats_rows=stats_rows, round_like_torch=rnd, accumulate=accumulate)
+        if res is not None:
+            return stats_rows, res[0], res[1]
     new_lp = _ops.policy_forward(fam, vd, latents, next_latents, k, old_log_probs, advantages, clip_range, adv_clip_max, kl_coeff,
                                  denom, stats_rows=stats_rows, round_like_torch=rnd, accumulate=accumulate)
     grad_v = _ops.policy_backward(fam, vd, latents, next_latents, new_lp, k, old_log_probs, advantages, clip_range, adv_clip_max,
