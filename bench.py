@@ -7,11 +7,11 @@ iteration's hot path for the prompt group(s) this rank owns, on synthetic random
 
   rollout        25 fused sampler steps (21 Euler-ODE + 4 SDE with log-prob), each reading a distinct
                  pre-generated model output v_i and writing all_latents[:, i+1] in place
-  exchange       ONE all_gather_into_tensor of the [3 models x 12] rewards          (N > 1 only)
-  advantages     group-relative, 3 reward models, weighted                         (1 launch)
+  exchange       ONE all-gather of the [3 models x 12] rewards                      (N > 1 only; default: fused with the
+  advantages     group-relative, 3 reward models, weighted                         (1 launch)   advantages into one peer-memory kernel)
   policy update  for each of the 4 window steps: fused log-prob + clipped-ratio loss forward, fused loss-grad +
                  log-prob backward -> grad wrt model output                        (2 launches each)
-  logging        ONE [4] all_reduce(AVG) of loss/policy/kl/clip_frac               (N > 1 only)
+  logging        ONE all_reduce(AVG) of the loss/policy/kl/clip_frac sums          (N > 1 only; default: one peer-memory kernel)
 
 metric  = sampler-step latent GB/s = algorithmic bytes of all sampler/log-prob kernels in the step
           (SURVEY.md §8d per-element figures) / step time, summed over ranks ("weak" scaling: each rank
@@ -524,7 +524,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); "
                                    "one prompt group per GPU", "io_dtypes": "model_output/noise bf16 in, latents/trajectory/log-prob fp32, grad bf16; arithmetic fp32", "group_size": B, "tokens": S, "channels": C, "sampling_steps": N_STEPS,
-                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "fused peer-memory kernels inside the step graph, no NCCL: reward gather + advantages (1 launch, st.global over NVLink + flags), [4x12x4] stats all-reduce (1 launch)" if peer_mode else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
+                       "sde_window": WINDOW, "reward_models": N_MODELS, "parallelism": f"dp{world} by prompt group", "collectives": ("none (N=1)" if world == 1 else "fused peer-memory kernels inside the step graph, no NCCL: reward gather + advantages (1 launch; 64-bit {call,value} words pushed into the peers' memory over NVLink), [4x12x4] stats all-reduce of the previous step (1 launch), both on a side branch of the graph" if peer_mode else "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " + ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows (in-graph NCCL measured 3.4x slower at N=8)")),
                        "l2": "inputs larger than L2: per step 157 MB model outputs + 25 MB noise + 327 MB trajectory + 25 MB grads", "launch": "CUDA graph per step"},
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
