@@ -489,7 +489,7 @@ def run_native(args):
         ms = a.elapsed_time(b)
         if args.profile_only:
             if rank == 0:
-                print(json.dumps({"profile_only": True, "steps": args.steps, "ms_per_step": ms / args.steps}), flush=True)
+                emit(json.dumps({"profile_only": True, "steps": args.steps, "ms_per_step": ms / args.steps}))
             if world > 1:
                 torch.cuda.synchronize(dev)
                 dist.barrier()
@@ -505,8 +505,8 @@ def run_native(args):
 
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"tuning_only": True, "n_gpus": world, "ms_per_step": ms_per_step, "value": value, "collectives": args.collectives,
-                              "in_graph": coll_in_graph, "policy": args.policy}), flush=True)
+            emit(json.dumps({"tuning_only": True, "n_gpus": world, "ms_per_step": ms_per_step, "value": value, "collectives": args.collectives,
+                              "in_graph": coll_in_graph, "policy": args.policy}))
         if world > 1:
             torch.cuda.synchronize(dev); dist.barrier(); os._exit(0)
         return
@@ -535,7 +535,7 @@ def run_native(args):
             "check": {"loss": loss_host, "e2e_loss": e2e_loss, "logp_mean": float(logps[:, window[0]].mean().item())},
             "library": mixgrpo_b200.library_path(),
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         # A live CUDA graph that holds captured NCCL kernels makes destroy_process_group() block at teardown (seen on
         # this image: the line was printed, then the ranks hung).  Drain, rendezvous once more, and leave without it.
@@ -609,10 +609,31 @@ def run_reference(args):
                        "device": "host CPU cores (reference PyTorch path)"},
             "rollout_steps_per_s": round(B * N_STEPS / cpu["s_per_step"], 2), "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_json_out = None
+
+
+def reserve_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle to the real stdout for it and point file descriptor 1 at
+    stderr, so nothing a library prints there (NCCL's version banner goes to stdout via printf whatever NCCL_DEBUG_FILE says)
+    can land next to it."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text: str):
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
