@@ -3,6 +3,7 @@
 // Each variant runs the flow SDE rollout arithmetic (bf16 v/eps, fp32 x -> fp32 x', x0, logp) over
 // rotating buffer sets (> L2) from a CUDA graph and prints us/launch and GB/s at 16 B/elem.
 #include <cuda_bf16.h>
+#include <string.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -574,6 +575,23 @@ int main(int argc, char** argv) {
     auto launch2 = [&](int i, cudaStream_t st) { k_copy<H_DEFAULT><<<(unsigned)((E / 8 + 255) / 256), 256, 0, st>>>(bufs[i].x, bufs[(i + 1) % NS].x, bufs[i].xo, bufs[i].x0, E); };
     us = time_graph(launch2, NS, REPS);
     printf("%-34s %7.2f us  %7.1f GB/s  %.3f\n", "copy2x default hints", us, E * 16 / us / 1e3, E * 16 / us / 1e3 / 6533.5);
+  }
+  if (argc > 3 && !strcmp(argv[3], "wave")) {
+    // one-wave shapes at (12,4096,64): every load of the launch is issued before the first CTA retires
+    run<8, 1, H_NC_NA, 7, 256, 6, 2>("packed + PDL b256 c6 u1 (1.73 waves)");
+    run<8, 2, H_NC_NA, 7, 224, 6, 2>("u2 b224 c6 (888 CTAs, 1.00 waves)");
+    run<8, 2, H_NC_NA, 7, 256, 6, 2>("u2 b256 c6 (768 CTAs)");
+    run<8, 2, H_NC_NA, 7, 256, 5, 2>("u2 b256 c5 (768 CTAs, 1.04 waves)");
+    run<8, 2, H_NC_NA, 7, 288, 5, 2>("u2 b288 c5 (684 CTAs)");
+    run<8, 2, H_NC_NA, 7, 352, 4, 2>("u2 b352 c4 (564 CTAs)");
+    run<8, 2, H_NC_NA, 7, 512, 3, 2>("u2 b512 c3 (384 CTAs)");
+    run<8, 3, H_NC_NA, 7, 256, 4, 2>("u3 b256 c4 (516 CTAs)");
+    run<8, 3, H_NC_NA, 7, 384, 3, 2>("u3 b384 c3 (348 CTAs)");
+    run<8, 4, H_NC_NA, 7, 256, 3, 2>("u4 b256 c3 (384 CTAs)");
+    run<8, 4, H_NC_NA, 7, 128, 6, 2>("u4 b128 c6 (768 CTAs)");
+    run<8, 4, H_NC_NA, 7, 128, 7, 2>("u4 b128 c7 (768 CTAs)");
+    run<8, 2, H_NC_NA, 0, 224, 6, 2>("u2 b224 c6 no reduction");
+    return 0;
   }
   run<8, 1, H_NC_NA, 7, 256, 6>("v8 u1 packed atomic (current)");
   run<8, 1, H_NC_NA, 7, 256, 6, 2>("packed + PDL b256 c6 (1.73 waves)");
