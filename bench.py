@@ -331,13 +331,18 @@ def measure_roofline(dev, peak_gbs, peak_kind):
 def e2e_run(w: Workload, window, steps: int, warmup: int):
     """Same step with HOST inputs: every step copies its 25 model outputs and the rewards from pinned host memory, runs
     through the public API (eager launches), and reads the stats rows + log-probs back.  The SDE noise is drawn on the
-    device, as in the reference (randn_tensor(..., device=model_output.device), SU:189-194) — it is not an input."""
+    device, as in the reference (randn_tensor(..., device=model_output.device), SU:189-194) — it is not an input.
+
+    The copies are pipelined the way a streaming caller would: two device input sets; while step k computes and its
+    results travel back, step k+1's inputs are already on the wire (copy stream, one event per tensor so sampler step i
+    only waits for ITS model output).  The first timed step's upload is NOT prefetched and the last one prefetches
+    nothing, so the timed region contains exactly `steps` uploads and `steps` read-backs."""
     hv = [torch.empty(B, S, C, dtype=torch.bfloat16).pin_memory() for _ in range(N_STEPS)]
     hr = torch.randn(N_MODELS, B).pin_memory()
     for t in hv:
         t.normal_()
-    dv = [torch.empty_like(t, device=w.dev) for t in hv]
-    dr = torch.empty(N_MODELS, B, device=w.dev)
+    sets = [{"dv": [torch.empty_like(t, device=w.dev) for t in hv], "dr": torch.empty(N_MODELS, B, device=w.dev), "evs": None}
+            for _ in range(2)]
     h_stats = torch.empty(WINDOW, B, 4).pin_memory()
     h_lp = torch.empty(B, N_STEPS).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in hv) + hr.numel() * 4
@@ -346,17 +351,24 @@ def e2e_run(w: Workload, window, steps: int, warmup: int):
     main = torch.cuda.current_stream(w.dev)
     gen = torch.Generator(device=w.dev).manual_seed(99)
 
-    def one():
-        # H2D on a copy stream, one event per tensor, so step i's kernel only waits for ITS model output
-        evs = []
-        copy_stream.wait_stream(main)
+    def upload(slot):
+        # the set was last read by the step before the previous one, which has completed (every step ends with a sync)
+        st, evs = sets[slot], []
         with torch.cuda.stream(copy_stream):
-            dr.copy_(hr, non_blocking=True)
+            st["dr"].copy_(hr, non_blocking=True)
             for i in range(N_STEPS):
-                dv[i].copy_(hv[i], non_blocking=True)
+                st["dv"][i].copy_(hv[i], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 evs.append(ev)
+        st["evs"] = evs
+
+    def one(k, prefetch_next):
+        slot = k % 2
+        if sets[slot]["evs"] is None:
+            upload(slot)
+        st = sets[slot]
+        evs, dv = st["evs"], st["dv"]
 
         class Lazy(list):
             def __getitem__(self, i):
@@ -364,18 +376,22 @@ def e2e_run(w: Workload, window, steps: int, warmup: int):
                 return dv[i]
         main.wait_event(evs[0])
         eps = [torch.randn(B, S, C, device=w.dev, dtype=torch.bfloat16, generator=gen) for _ in range(WINDOW)]
-        stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=eps, rewards=dr)
+        stats, logps, _ = native_step(w, window, v_list=Lazy(), eps=eps, rewards=st["dr"])
+        if prefetch_next:
+            upload(1 - slot)
         h_stats.copy_(stats, non_blocking=True)
         h_lp.copy_(logps, non_blocking=True)
         main.synchronize()
+        st["evs"] = None
         return float(h_stats.sum(dim=(0, 1))[0])
 
-    for _ in range(warmup):
-        one()
+    for k in range(warmup):
+        one(k, prefetch_next=k + 1 < warmup)
+    torch.cuda.synchronize(w.dev)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        loss = one()
+    for k in range(steps):
+        loss = one(k, prefetch_next=k + 1 < steps)
     torch.cuda.synchronize(w.dev)
     dt = time.perf_counter() - t0
     return dt / steps, h2d, d2h, loss
@@ -529,7 +545,7 @@ def run_native(args):
             "rollout_steps_per_s": round(B * N_STEPS * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": algorithmic_bytes_per_step(),
             "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages + rollout.policy_update (eager launches)"},
+                    "ms_per_step": round(e2e_s * 1e3, 3), "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages (peer.PeerExchange.gather_advantages at N > 1) + rollout.policy_update, eager launches; uploads double-buffered so step k+1's inputs travel while step k computes"},
             "gpu_launches": (LAUNCHES_PER_STEP + (1 if peer_mode else 0)) * args.steps,
             "clocks": clk.summary(), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "check": {"loss": loss_host, "e2e_loss": e2e_loss, "logp_mean": float(logps[:, window[0]].mean().item())},
