@@ -440,6 +440,7 @@ def run_native(args):
     peer_mode = world > 1 and args.collectives == "peer"
     if peer_mode:
         from mixgrpo_b200.peer import PeerExchange
+        mixgrpo_b200._cabi.lib().mixgrpo_set_tuning(2, 60000)      # a lost peer fails the bench after 60 s instead of 10 min
         try:
             w.px = PeerExchange()
             failed = 0

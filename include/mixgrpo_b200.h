@@ -243,7 +243,7 @@ int mixgrpo_grpo_loss(const float* new_logp, const float* old_logp, const float*
  * regions_host[q] is rank q's region as mapped in the CALLING process (its own allocation at [rank]).  All ranks
  * must issue the same sequence of exchange calls (collective semantics); the call counter lives in the region, so
  * the launches are CUDA-graph capturable.  A wait that exceeds the timeout (mixgrpo_set_tuning key 2, default
- * 30 s) sets the region's status word and yields NaN outputs instead of hanging the GPU.
+ * 10 min, the order of NCCL's watchdog: ranks may be skewed by a slow reward model) sets the region's status word and yields NaN outputs instead of hanging the GPU.
  * Several "ranks" may live on ONE device (regions_host = plain device pointers, one stream per rank): that is how
  * the single-GPU parity tests drive the protocol. */
 #define MIXGRPO_PEER_MAX_WORLD 16

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const __gr
   peer_commit(p.peer, 1, call);
 }
 
-static unsigned long long g_peer_timeout_ms = 30000ull;   // mixgrpo_set_tuning key 2 (0 = wait forever)
+static unsigned long long g_peer_timeout_ms = 600000ull;   // mixgrpo_set_tuning key 2 (0 = wait forever); 10 min like NCCL's watchdog
 
 static int fill_peer(PeerArgs& a, void* const* regions_host, int rank, int world, int64_t cap) {
   if (!regions_host || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || cap < 1) return MIXGRPO_EINVAL;
