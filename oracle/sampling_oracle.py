@@ -82,6 +82,18 @@ def flow_step(v, x, eta, sigmas, index, x_next=None, noise=None, determistic=Fal
     return x_next, x0, logp, mean, scale
 
 
+def gauss_logp_fp64(x_next, mean, scale, constants=True):
+    """fp64 "truth" of the log-prob reduction (SU:201-208) for GIVEN fp32 tensors ``x_next`` / ``mean`` and the fp32
+    scalar ``scale``: every element widened to double before it is squared and averaged.  Used for error budgeting
+    (SURVEY §7 stage 1): the reference's fp32 ``mean()`` and the kernel's fixed-point reduction are both compared to it."""
+    s = torch.as_tensor(scale, dtype=torch.float32).double()
+    d = x_next.double() - mean.double()
+    q = (-(d ** 2) / (2 * s ** 2)).reshape(d.shape[0], -1).mean(dim=1)
+    if constants:
+        q = q - torch.log(s) - math.log(math.sqrt(2 * math.pi))
+    return q
+
+
 def dance_step(v, x, eta, sigmas, index, x_next=None, noise=None, grpo=True, sde_solver=True):
     """DanceGRPO flux_step, SU:212-253.  ``noise`` (fp32, SU:238 randn_like) is used
     only when rolling out with sde_solver.  The log-prob constants are NOT subtracted

@@ -5,6 +5,7 @@ BIT-EXACT tensors for flow/dance and ≤1e-5 for dpm (exp/log of the coefficient
 host libm and torch); log_prob / loss ≤1e-4 rel; advantages ≤1e-6.
 """
 import itertools
+import math
 import types
 
 import pytest
@@ -576,3 +577,24 @@ def test_extended_mode_group_split_across_ranks_single_process():
     assert torch.allclose(full.cpu(), ref, atol=2e-6)
     for rank in range(8):
         assert torch.allclose(grpo.split_group_slice(full, rank, 8).cpu(), ref[rank * 3:(rank + 1) * 3], atol=2e-6)
+
+
+@pytest.mark.parametrize("B,S", [(12, 4096), (24, 1024), (4, 256)])
+def test_logprob_reduction_error_budget_vs_fp64_truth(B, S):
+    """Error budgeting (SURVEY §7 stage 1): with bit-identical x_next / mean tensors, the kernel's deterministic fixed-point
+    reduction must be at least as close to the fp64 truth as the reference's own fp32 ``mean()`` is — up to one fp32 ulp of
+    the result, the resolution of the value both return."""
+    from mixgrpo_b200 import sampling_utils as su
+    d = _dev()
+    x, v, eps, _ = _inputs(B, S, torch.bfloat16, seed=77)
+    for idx in (1, 9, 20):
+        o_xn, _, o_lp, o_mean, o_scale = O.flow_step(v, x, ETA, SIG, idx, None, eps, False)
+        xn, _, lp, mean, scale = su.flow_grpo_step(v.to(d), x.to(d), ETA, SIG, idx, None, noise=eps.to(d), rounding="ref_cpu")
+        assert torch.equal(xn.cpu(), o_xn) and torch.equal(mean.cpu(), o_mean)
+        truth = O.gauss_logp_fp64(o_xn, o_mean, o_scale)
+        err_gpu = (lp.cpu().double() - truth).abs()
+        err_ref = (o_lp.double() - truth).abs()
+        # the result is a difference of O(1) terms (-q - log s - log sqrt(2 pi)): one ulp of the largest term
+        ulp = torch.finfo(torch.float32).eps * (0.5 + abs(math.log(float(o_scale))) + 0.92)
+        assert (err_gpu <= err_ref + ulp).all(), (idx, err_gpu.max().item(), err_ref.max().item())
+        assert (err_gpu <= 2 * ulp).all(), (idx, err_gpu.max().item())
