@@ -101,8 +101,14 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
         raise ValueError(f"mixgrpo_b200: model_output {tuple(v.shape)} and latents {tuple(x.shape)} differ")
     v = v if v.is_contiguous() else v.contiguous()
     B = v.shape[0]
-    n = v[0].numel()
     dev = v.device
+    if B == 0:
+        # empty batch: every reference op is a no-op on empty tensors and the per-sample log-prob is an empty [0] vector
+        f32 = lambda: torch.empty(v.shape, dtype=torch.float32, device=dev)   # noqa: E731
+        return ((x_next if src == SRC_GIVEN else (out_x_next if out_x_next is not None else f32())), f32() if want_x0 else None,
+                (out_logp if out_logp is not None else torch.empty((0,), dtype=torch.float32, device=dev)) if want_logp else None,
+                f32() if want_mean else None)
+    n = v[0].numel()
     x, x_bs = _rows(x, "latents")
     noise_p = in_p = m1_p = m2_p = None
     in_bs = n
@@ -201,6 +207,8 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
         _require_cuda(t, nm)
     vd = _dtype_code(v, "model_output")
     v = v if v.is_contiguous() else v.contiguous()
+    if v.shape[0] == 0:
+        return out if out is not None else torch.empty_like(v)
     B, n = v.shape[0], v[0].numel()
     x, x_bs = _rows(x.to(torch.float32), "latents")
     x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
@@ -251,6 +259,8 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
         _require_cuda(t, nm)
     vd = _dtype_code(v, "model_output")
     v = v if v.is_contiguous() else v.contiguous()
+    if v.shape[0] == 0:
+        return out_logp if out_logp is not None else torch.empty((0,), dtype=torch.float32, device=v.device)
     B, n, dev = v.shape[0], v[0].numel(), v.device
     x, x_bs = _rows(x.to(torch.float32), "latents")
     x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
@@ -279,6 +289,8 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
         _require_cuda(t, nm)
     vd = _dtype_code(v, "model_output")
     v = v if v.is_contiguous() else v.contiguous()
+    if v.shape[0] == 0:
+        return torch.empty_like(v)
     B, n, dev = v.shape[0], v[0].numel(), v.device
     x, x_bs = _rows(x.to(torch.float32), "latents")
     x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
@@ -307,6 +319,8 @@ def policy_step(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Ten
         _require_cuda(t, nm)
     vd = _dtype_code(v, "model_output")
     v = v if v.is_contiguous() else v.contiguous()
+    if v.shape[0] == 0:
+        return torch.empty((0,), dtype=torch.float32, device=v.device), torch.empty_like(v)
     B, n, dev = v.shape[0], v[0].numel(), v.device
     x, x_bs = _rows(x.to(torch.float32), "latents")
     x_next, in_bs = _rows(x_next.to(torch.float32), "prev_sample")
@@ -355,6 +369,8 @@ def group_advantages(rewards: torch.Tensor, weights: Optional[torch.Tensor], num
         r = r.unsqueeze(0)
     r = r.contiguous()
     n_models, local_B = r.shape
+    if local_B == 0:
+        return torch.empty((0,), dtype=torch.float32, device=r.device)
     w_p = None
     if weights is not None:
         weights = weights.to(device=r.device, dtype=torch.float32).contiguous()

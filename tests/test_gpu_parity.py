@@ -598,3 +598,22 @@ def test_logprob_reduction_error_budget_vs_fp64_truth(B, S):
         ulp = torch.finfo(torch.float32).eps * (0.5 + abs(math.log(float(o_scale))) + 0.92)
         assert (err_gpu <= err_ref + ulp).all(), (idx, err_gpu.max().item(), err_ref.max().item())
         assert (err_gpu <= 2 * ulp).all(), (idx, err_gpu.max().item())
+
+
+def test_empty_batch_is_a_noop_like_the_reference():
+    """B == 0: the reference's ops run on empty tensors (empty outputs, empty [0] log-prob); nothing is launched here."""
+    from mixgrpo_b200 import grpo, ops, rollout as R, sampling_utils as su
+    d = _dev()
+    x = torch.zeros(0, 16, 64, device=d)
+    v = torch.zeros(0, 16, 64, device=d, dtype=torch.bfloat16)
+    before = ops.launch_count
+    xn, x0, lp, mean, _ = su.flow_grpo_step(v, x, ETA, SIG, 3, None, noise=v)
+    o = O.flow_step(v.cpu(), x.cpu(), ETA, SIG, 3, None, v.cpu(), False)
+    assert xn.shape == o[0].shape and x0.shape == o[1].shape and lp.shape == o[2].shape == (0,) and mean.shape == o[3].shape
+    _, _, lp2 = su.dance_grpo_step(v, x, ETA, SIG, 3, x, True, True)
+    assert lp2.shape == (0,)
+    _, nl, gv = R.policy_update(v, x, x, torch.zeros(0, device=d), torch.zeros(0, device=d), SIG, 3, R.SamplerConfig(), clip_range=1e-4,
+                                adv_clip_max=5.0, kl_coeff=0.0, gradient_accumulation_steps=1, num_train_timesteps=1)
+    assert nl.shape == (0,) and gv.shape == v.shape and gv.dtype == v.dtype
+    assert grpo.compute_group_advantages(torch.zeros(0, device=d), 4).shape == (0,)
+    assert ops.launch_count == before
