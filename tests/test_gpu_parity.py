@@ -617,3 +617,33 @@ def test_empty_batch_is_a_noop_like_the_reference():
     assert nl.shape == (0,) and gv.shape == v.shape and gv.dtype == v.dtype
     assert grpo.compute_group_advantages(torch.zeros(0, device=d), 4).shape == (0,)
     assert ops.launch_count == before
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_full_size_dance_and_flash_dpm_vs_reference_ops_on_device(dtype):
+    """BASELINE configs[1] shape (12, 4096, 64) for the other two operator families: DanceGRPO's flux_step and the
+    MixGRPO-Flash DPM-Solver++ order-2 midpoint ODE steps (configs[3]), against the reference's op sequence executed on the
+    same B200 (oracle functions on CUDA tensors, default CUDA rounding mode)."""
+    from mixgrpo_b200 import sampling_utils as su
+    d = _dev()
+    B, S = 12, 4096
+    g = torch.Generator(device=d).manual_seed(4242)
+    x = torch.randn(B, S, 64, device=d, generator=g)
+    v = torch.randn(B, S, 64, device=d, generator=g).to(dtype)
+    nz = torch.randn(B, S, 64, device=d, generator=g)
+    sig = SIG.to(d)
+    for idx, sde in ((0, True), (9, True), (24, True), (5, False)):
+        out = su.dance_grpo_step(v, x, ETA, sig, idx, None, True, sde, noise=nz)
+        ref = O.dance_step(v, x, ETA, sig, idx, None, nz, True, sde)
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]), (idx, sde)
+        assert torch.allclose(out[2], ref[2], rtol=1e-5, atol=1e-12), (idx, sde)
+    args = types.SimpleNamespace(dpm_algorithm_type="dpmsolver++", dpm_solver_type="midpoint", dpm_solver_order=2)
+    st, oh = su.DPMState(order=2), O.History(2)
+    xs = x
+    for idx in (10, 11, 12, 24):                                  # order 1 (empty history), order 2, order 2, final step (order 1)
+        out = su.dpm_step(args, v, xs, idx, sig[:-1], sig, dpm_state=st, sde_solver=False)
+        ref = O.dpm_step(v, xs, idx, 25, sig, algo="dpmsolver++", solver_order=2, solver_type="midpoint", history=oh, noise=None, sde_solver=False)
+        assert torch.equal(out[1], ref[1]), f"x0 step {idx}"
+        assert _rel(out[0], ref[0]) < 1e-5, f"x_next step {idx}"
+        assert st.lower_order_nums == oh.lower_order_nums
+        xs = ref[0]
