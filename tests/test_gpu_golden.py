@@ -202,3 +202,39 @@ def test_rollout_dropin_and_native_vs_oracle(name):
         fin = torch.isfinite(rlp)
         assert torch.allclose(lp[fin], rlp[fin], rtol=2e-3, atol=1e-3), name                    # ODE-step values (unused)
     assert nat[4].numel() == ref[2].shape[1]
+
+
+@pytest.mark.parametrize("name", ["mixgrpo_w4_8", "flash_mid_04"])
+def test_full_size_rollouts_vs_reference_ops_on_device(name):
+    """BASELINE configs[1] / configs[3] at FULL size — group 12, (4096, 64) latents, 25 steps (MixGRPO window 4; Flash with
+    the compressed DPM-Solver++ tail) — through the batched driver, against the reference's op sequence rolled out on the
+    same B200 (oracle.rollout on CUDA tensors, default CUDA rounding).  Trajectory bit-exact for MixGRPO."""
+    from mixgrpo_b200 import rollout as R
+    args, window = _cases()[name]
+    det = [i not in window for i in range(N)]
+    g = torch.Generator(device=DEV).manual_seed(11)
+    Br, Sr = 12, 4096
+    z0 = torch.randn(Br, Sr, 64, device=DEV, generator=g).bfloat16()
+    noises = [torch.randn(Br, Sr, 64, device=DEV, generator=g).bfloat16() for i in range(N)]   # the reference draws noise on ODE steps too (SU:188-195)
+    model = ExactStandIn().to(DEV)
+
+    def gpu_model(zz, s, i):
+        return model(zz, None, torch.full([Br], int(float(s) * 1000), device=DEV) / 1000, None, None, None, None, None, False)[0]
+
+    ref = O.rollout(gpu_model, z0, SIG.to(DEV), det, noises, eta=args.eta, shift=args.shift, flow_grpo_sampling=args.flow_grpo_sampling,
+                    dpm_algorithm_type=args.dpm_algorithm_type, dpm_apply_strategy=args.dpm_apply_strategy,
+                    dpm_post_compress_ratio=args.dpm_post_compress_ratio, dpm_solver_order=args.dpm_solver_order,
+                    dpm_solver_type=args.dpm_solver_type, drop_last_sample=args.drop_last_sample)
+    cfg = R.SamplerConfig(sampling_steps=N, eta=args.eta, shift=args.shift, flow_grpo_sampling=args.flow_grpo_sampling,
+                          dpm_algorithm_type=args.dpm_algorithm_type, dpm_apply_strategy=args.dpm_apply_strategy,
+                          dpm_post_compress_ratio=args.dpm_post_compress_ratio, dpm_solver_order=args.dpm_solver_order,
+                          dpm_solver_type=args.dpm_solver_type, drop_last_sample=args.drop_last_sample)
+    nat = R.rollout(gpu_model, z0, SIG, det, cfg, noises=noises)
+    assert nat[2].shape == ref[2].shape and nat[3].shape == ref[3].shape
+    if args.dpm_algorithm_type == "null":
+        assert torch.equal(nat[2], ref[2]) and torch.equal(nat[0], ref[0].float()), name
+    else:
+        assert ((nat[2] - ref[2]).norm() / ref[2].norm()).item() < 1e-5, name
+    sde_cols = [i for i in range(ref[3].shape[1]) if i < N and not det[i]]
+    assert sde_cols
+    assert torch.allclose(nat[3][:, sde_cols], ref[3][:, sde_cols], rtol=1e-5, atol=0), name
