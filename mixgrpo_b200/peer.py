@@ -16,6 +16,7 @@ state is kernels pushing floats into peers' memory.  Every launch is CUDA-graph 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -38,6 +39,9 @@ class PeerExchange:
     def __init__(self, group: Optional[dist.ProcessGroup] = None, cap_floats: int = 4096,
                  device: Optional[torch.device] = None, *, _regions: Optional[Sequence[int]] = None,
                  _rank: Optional[int] = None):
+        if os.environ.get("MIXGRPO_PEER_DISABLE") == "1" and _regions is None:
+            # operator switch (same value on every rank): callers fall back to NCCL (grpo.gather_rewards / reduce_step_stats)
+            raise RuntimeError("mixgrpo_b200: PeerExchange disabled by MIXGRPO_PEER_DISABLE=1")
         self._lib = _cabi.lib()
         self.cap = int(cap_floats)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
