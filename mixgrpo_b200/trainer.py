@@ -7,6 +7,9 @@ models are out of scope; what is here is exactly the code betwee
 * ``sample_reference_model``   TR:184-329  — rollout orchestration, but the whole prompt group runs as ONE batch
                                              (the reference loops 12 batch-1 rollouts, TR:213,231); VAE decode + reward
                                              models are a caller-supplied callback
+* ``train_one_step``           TR:341-640  — the whole hot path of one training step as one call (rollout → reward exchange +
+                                             advantages → re-ranging → policy-update loop → logging reduction); optional fused
+                                             NVLink exchange (``peer.PeerExchange``)
 * ``train_window``             TR:503-615  — the (sample, window step) policy-update loop: DiT forward with grad, fused
                                              log-prob + loss forward, fused backward, ``pred.backward(grad)``; logging
                                              scalars stay on the device
@@ -105,12 +108,16 @@ def sample_reference_model(args, device, transformer, encoder_hidden_states, poo
 def train_window(args, transformer, samples: Dict, advantages: torch.Tensor, sigma_schedule: torch.Tensor,
                  train_timesteps: Sequence[int], encoder_hidden_states, pooled_prompt_embeds, text_ids, image_ids, *,
                  micro_batch: int = 1, on_accumulated: Optional[Callable[[int], None]] = None,
-                 stats_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 stats_rows: Optional[torch.Tensor] = None, order: Optional[Sequence[int]] = None,
+                 perms: Optional[Sequence[Sequence[int]]] = None) -> torch.Tensor:
     """TR:536-615 without host syncs: for every micro-batch of samples and every window step — DiT forward with grad on
     the stored latent, fused log-prob + clipped-ratio loss (forward and backward: two launches), ``pred.backward(grad)``.
 
-    ``samples`` is ``rollout.make_samples(...)`` (TR:406-415).  ``on_accumulated(i)`` is called after sample ``i`` when
-    ``(i + 1) % gradient_accumulation_steps == 0`` — the place of clip_grad_norm_/optimizer.step() (TR:605-609).
+    ``samples`` is ``rollout.make_samples(...)`` (TR:406-415).  ``on_accumulated(i)`` is called after the ``i``-th trained
+    sample when ``(i + 1) % gradient_accumulation_steps == 0`` — the place of clip_grad_norm_/optimizer.step() (TR:605-609).
+    ``order``: which samples to train and in which order (``balance_pos_neg`` re-ranging, TR:528-535); default all, in
+    place.  ``perms`` (host lists, ``training_strategy == "all"``, TR:503-509): ``samples`` columns were permuted per
+    sample, so column ``t`` of sample ``i`` is sampler step ``perms[i][t]`` — needs ``micro_batch == 1``.
     Returns ``stats_rows`` ([B, 4]: per-sample sums of loss, policy_loss, kl_loss, clip_frac over the window)."""
     B = samples["latents"].shape[0]
     dev = samples["latents"].device
@@ -120,20 +127,96 @@ def train_window(args, transformer, samples: Dict, advantages: torch.Tensor, sig
                                  flow_grpo_sampling=args.flow_grpo_sampling)
     transformer.train()
     T = len(train_timesteps)
-    for lo in range(0, B, micro_batch):
-        hi = min(lo + micro_batch, B)
+    if perms is not None and micro_batch != 1:
+        raise ValueError("per-sample step permutations (training_strategy 'all') need micro_batch == 1")
+    order = list(range(B)) if order is None else [int(i) for i in order]
+    contiguous = order == list(range(B))
+    for lo in range(0, len(order), micro_batch):
+        ids = order[lo:lo + micro_batch]
+        # a run of consecutive samples is a view; a re-ranged micro-batch is gathered (one small index copy per tensor)
+        sel = slice(ids[0], ids[-1] + 1) if (contiguous or len(ids) == 1) else torch.tensor(ids, device=dev)
         for t in train_timesteps:
-            lat = samples["latents"][lo:hi, t]
-            pred = _forward(transformer, lat, encoder_hidden_states[lo:hi], pooled_prompt_embeds[lo:hi], text_ids[lo:hi], image_ids,
-                            samples["timesteps"][lo:hi, t])
-            _, _, grad = _rollout.policy_update(pred, lat, samples["next_latents"][lo:hi, t], samples["log_probs"][lo:hi, t],
-                                                advantages[lo:hi], sigma_schedule, t, cfg, clip_range=args.clip_range,
+            step = int(perms[ids[0]][t]) if perms is not None else t               # TR:553
+            lat = samples["latents"][sel, t]
+            rows = stats_rows[sel] if isinstance(sel, slice) else torch.zeros(len(ids), 4, dtype=torch.float32, device=dev)
+            pred = _forward(transformer, lat, encoder_hidden_states[sel], pooled_prompt_embeds[sel], text_ids[sel], image_ids,
+                            samples["timesteps"][sel, t])
+            _, _, grad = _rollout.policy_update(pred, lat, samples["next_latents"][sel, t], samples["log_probs"][sel, t],
+                                                advantages[sel], sigma_schedule, step, cfg, clip_range=args.clip_range,
                                                 adv_clip_max=args.adv_clip_max, kl_coeff=args.kl_coeff,
                                                 gradient_accumulation_steps=args.gradient_accumulation_steps,
-                                                num_train_timesteps=T, stats_rows=stats_rows[lo:hi])
+                                                num_train_timesteps=T, stats_rows=rows)
+            if not isinstance(sel, slice):
+                stats_rows.index_add_(0, sel, rows)
             pred.backward(grad)                                                      # TR:585 continues into the DiT
         if on_accumulated is not None:
-            for i in range(lo, hi):
+            for i in range(lo, lo + len(ids)):
                 if (i + 1) % args.gradient_accumulation_steps == 0:
                     on_accumulated(i)
     return stats_rows
+
+
+def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.Tensor], object], timesteps_train: Sequence[int],
+                   reward_weights, encoder_hidden_states, pooled_prompt_embeds, text_ids, *, exchange=None,
+                   on_accumulated: Optional[Callable[[int], None]] = None, micro_batch: int = 1,
+                   input_latents: Optional[torch.Tensor] = None, noises=None, generator: Optional[torch.Generator] = None,
+                   rng=None):
+    """The hot path of the reference's ``train_one_step`` (TR:341-640) as one call: prompt repetition (TR:369-384), batched
+    rollout (TR:386-399), sample bookkeeping (TR:400-415), reward exchange + group-relative advantages (TR:417-501), step
+    permutation / positive-negative re-ranging (TR:503-535), the (sample, window step) policy-update loop (TR:536-615) and
+    the logging reduction (TR:586-600, 617-625).  What is NOT here is what SURVEY §8 leaves on stock PyTorch: the data
+    loader (``next(loader)`` → pass its tensors), VAE decode + reward models (``decode_and_score``), and
+    ``clip_grad_norm_`` / ``optimizer.step()`` / ``lr_scheduler.step()`` (``on_accumulated``, called where TR:605-609 runs them).
+
+    ``exchange``: a :class:`mixgrpo_b200.peer.PeerExchange` — reward gather + advantages and the logging all-reduce then
+    run as one fused NVLink kernel each; without it NCCL (or nothing, single process) is used.
+    Returns ``(stats [4] = total_loss, policy_total_loss, kl_total_loss, total_clip_frac — rank-averaged device tensor,
+    gathered_reward_res (per-model mean of the gathered rewards, device tensors), samples, advantages)``; nothing syncs the
+    host except the optional ``advantage_rerange_strategy`` (which needs the advantages' signs, like the reference)."""
+    G = int(args.num_generations)
+    if getattr(args, "use_group", True):                                             # TR:369-384
+        rep = lambda t: None if t is None else torch.repeat_interleave(t, G, dim=0)   # noqa: E731
+        encoder_hidden_states, pooled_prompt_embeds, text_ids = rep(encoder_hidden_states), rep(pooled_prompt_embeds), rep(text_ids)
+    rewards, all_latents, all_log_probs, sigma_schedule, image_ids = sample_reference_model(
+        args, device, transformer, encoder_hidden_states, pooled_prompt_embeds, text_ids, decode_and_score, timesteps_train,
+        input_latents=input_latents, generator=generator, noises=noises)
+    samples = _rollout.make_samples(all_latents, all_log_probs, sigma_schedule, args.sampling_steps)        # TR:400-415
+    rewards = {k: v.to(torch.float32) for k, v in rewards.items()} if isinstance(rewards, dict) else rewards.to(torch.float32)
+    use_group = getattr(args, "use_group", True)
+    trimmed = float(getattr(args, "trimmed_ratio", 0.0) or 0.0)
+    if exchange is not None:                                                         # TR:417-501 in ONE launch
+        advantages, gathered = exchange.gather_advantages(rewards, G, reward_weights, trimmed_ratio=trimmed,
+                                                          mode="local" if use_group else "global")
+    else:
+        gathered = _grpo.gather_rewards(rewards)
+        advantages = _grpo.compute_group_advantages(rewards, G, reward_weights, trimmed_ratio=trimmed, use_group=use_group,
+                                                    gathered_rewards=None if use_group else gathered)
+    samples["rewards"], samples["advantages"] = rewards, advantages
+    B = all_latents.shape[0]
+    perms_host, order = None, None
+    strategy = getattr(args, "training_strategy", "part")
+    if strategy == "all":                                                            # TR:503-509, TR:518-525
+        perms = _rollout.shuffle_timesteps(samples, generator=None)
+        perms_host = perms.tolist()
+        n_cols = samples["timesteps"].shape[1]
+        frozen = int(getattr(args, "frozen_init_timesteps", 0) or 0)
+        train_timesteps = range(frozen) if frozen > 0 else range(int(n_cols * float(getattr(args, "timestep_fraction", 1.0))))
+        micro_batch = 1
+    else:
+        train_timesteps = list(timesteps_train)
+        rerange = getattr(args, "advantage_rerange_strategy", "null")
+        if rerange in ("random", "balance"):                                         # TR:527-535 (host decision, like the reference)
+            tagged = [{"index": i, "advantages": a} for i, a in enumerate(advantages.tolist())]
+            order = [d["index"] for d in _rollout.balance_pos_neg(tagged, use_random=rerange == "random", rng=rng)]
+        elif rerange != "null":
+            raise ValueError(f"advantage_rerange_strategy {rerange} is not supported.")
+    rows = train_window(args, transformer, samples, advantages, sigma_schedule, train_timesteps, encoder_hidden_states,
+                        pooled_prompt_embeds, text_ids, image_ids, micro_batch=micro_batch, on_accumulated=on_accumulated,
+                        order=order, perms=perms_host)
+    stats = rows.sum(dim=0)                                                          # TR:588-600 add these up one .item() at a time
+    stats = exchange.allreduce_stats(stats) if exchange is not None else _grpo.reduce_step_stats(stats)
+    if isinstance(gathered, dict):                                                   # TR:617-625
+        gathered_res = {k: v.mean() for k, v in gathered.items()}
+    else:
+        gathered_res = gathered.mean()
+    return stats, gathered_res, samples, advantages

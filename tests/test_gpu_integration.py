@@ -164,3 +164,61 @@ def test_config0_flash_rollout_with_tiny_transformer():
     assert torch.equal(all_lat[:, :5], ref[2][:, :5])                                     # Euler + SDE part: bit-exact
     assert ((all_lat - ref[2]).norm() / ref[2].norm()) < 1e-5                             # DPM tail: host vs device exp/log
     assert torch.allclose(all_lp[:, window], ref[3][:, window], rtol=1e-5, atol=0)
+
+
+def test_config0_train_one_step_composition():
+    """trainer.train_one_step (the hot path of TR:341-640 as one call) equals its pieces composed by hand (the test above
+    pins those to the reference path), with NCCL-free single-process statistics and with a PeerExchange endpoint."""
+    import random
+    from mixgrpo_b200 import grpo, rollout as R, trainer
+    from mixgrpo_b200.peer import PeerExchange
+    args = _args(use_group=True, multi_reward_mix="advantage_aggr", advantage_rerange_strategy="null", trimmed_ratio=0.0)
+    model, enc, pooled, text_ids, lat0, noises, rewards = _setup(1)
+    weights = {"hps": 1.0, "pick": 0.5}
+    enc1, pooled1, tid1 = enc[:1], pooled[:1], text_ids[:1]                       # ONE prompt, repeated num_generations times (TR:369-384)
+    enc_r, pooled_r, tid_r = (t.repeat_interleave(G, dim=0) for t in (enc1, pooled1, tid1))
+    # ---- by hand
+    model.eval()
+    rew, all_lat, all_lp, sig, image_ids = trainer.sample_reference_model(args, DEV, model, enc_r, pooled_r, tid_r, lambda lat: rewards, WINDOW,
+                                                                          input_latents=lat0, noises=noises)
+    adv = grpo.compute_group_advantages(rew, G, weights)
+    samples = R.make_samples(all_lat, all_lp, sig, N)
+    model.zero_grad(set_to_none=True)
+    rows = trainer.train_window(args, model, samples, adv, sig, WINDOW, enc_r, pooled_r, tid_r, image_ids)
+    want_stats = rows.sum(dim=0)
+    want_grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    assert len(want_grads) > 30 and torch.isfinite(want_stats).all()
+    # ---- one call, without and with the fused exchange endpoint (world size 1: same kernels, no peers)
+    px = PeerExchange()
+    try:
+        for exchange in (None, px):
+            model.zero_grad(set_to_none=True)
+            calls = []
+            stats, gathered_res, samples2, adv2 = trainer.train_one_step(
+                args, DEV, model, lambda lat: rewards, WINDOW, weights, enc1, pooled1, tid1, exchange=exchange, on_accumulated=calls.append,
+                input_latents=lat0, noises=noises)
+            assert calls == [1, 3]
+            assert torch.equal(adv2, adv) and torch.equal(samples2["latents"], samples["latents"])
+            assert torch.allclose(stats, want_stats, rtol=1e-6, atol=1e-9), (stats, want_stats)
+            assert set(gathered_res) == {"hps", "pick"} and torch.allclose(gathered_res["pick"], rewards["pick"].mean())
+            params = dict(model.named_parameters())
+            for n, g_ref in want_grads.items():
+                err = (params[n].grad - g_ref).norm() / g_ref.norm().clamp_min(1e-20)
+                assert err < 1e-5, (n, err.item())
+        # ---- positive/negative re-ranging (TR:527-535): zero-advantage samples are dropped, the rest interleaved
+        args_b = _args(use_group=True, advantage_rerange_strategy="balance", trimmed_ratio=0.0)
+        model.zero_grad(set_to_none=True)
+        calls = []
+        stats_b, _, _, adv_b = trainer.train_one_step(args_b, DEV, model, lambda lat: rewards, WINDOW, weights, enc1, pooled1, tid1, exchange=px,
+                                                      on_accumulated=calls.append, input_latents=lat0, noises=noises, rng=random.Random(0))
+        assert torch.equal(adv_b, adv) and torch.isfinite(stats_b).all()
+        assert torch.allclose(stats_b, want_stats, rtol=1e-4, atol=1e-7)            # same samples, another order (none has advantage 0)
+        # ---- training_strategy "all" (DanceGRPO style, TR:503-525): per-sample step permutation, a fraction of the steps
+        args_a = _args(use_group=True, training_strategy="all", timestep_fraction=0.5, frozen_init_timesteps=0)
+        model.zero_grad(set_to_none=True)
+        stats_a, _, samples_a, _ = trainer.train_one_step(args_a, DEV, model, lambda lat: rewards, WINDOW, weights, enc1, pooled1, tid1,
+                                                          input_latents=lat0, noises=[n for n in noises])
+        assert samples_a["latents"].shape == samples["latents"].shape and torch.isfinite(stats_a).all()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    finally:
+        px.close()
