@@ -78,6 +78,35 @@ def main():
         assert torch.equal(gathered["ir"].cpu(), torch.cat([rewards_of(q, 100 + it)["ir"] for q in range(world)]))
         want = torch.tensor([1.0, 2.0, 3.0, 4.0]) * (sum(q + it for q in range(world)) / world)
         assert torch.allclose(st.cpu(), want, rtol=1e-6)
+    # end to end: one training step (BASELINE configs[0] shape: tiny FLUX-shaped transformer, 256^2 latents, group 4) per rank, with NCCL
+    # collectives and with the fused exchange — same advantages, same local gradients, same rank-averaged statistics
+    import types
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from tiny_flux import TinyFluxTransformer
+    from mixgrpo_b200 import trainer
+    targs = types.SimpleNamespace(w=256, h=256, sampling_steps=10, shift=3.0, eta=0.7, flow_grpo_sampling=True, dpm_algorithm_type="null",
+                                  dpm_apply_strategy="post", dpm_post_compress_ratio=0.4, dpm_solver_order=2, dpm_solver_type="midpoint",
+                                  sample_strategy="progressive", drop_last_sample=False, training_strategy="part", init_same_noise=False,
+                                  clip_range=1e-4, adv_clip_max=5.0, kl_coeff=0.01, gradient_accumulation_steps=2, num_generations=4,
+                                  use_group=True, advantage_rerange_strategy="null", trimmed_ratio=0.0)
+    torch.manual_seed(0)
+    model = TinyFluxTransformer().to(dev)
+    gg = torch.Generator(device=dev).manual_seed(77 + rank)
+    enc, pooled, tids = torch.randn(1, 6, 32, device=dev, generator=gg), torch.randn(1, 16, device=dev, generator=gg), torch.zeros(1, 3, device=dev)
+    lat0 = torch.randn(4, 16, 32, 32, device=dev, generator=gg).bfloat16()
+    nzs = [torch.randn(4, 256, 64, device=dev, generator=gg).bfloat16() for _ in range(10)]
+    rw = {"hps": torch.randn(4, device=dev, generator=gg), "pick": torch.randn(4, device=dev, generator=gg)}
+    res = []
+    for exchange in (None, px):
+        model.zero_grad(set_to_none=True)
+        stats, gres, _, adv_t = trainer.train_one_step(targs, dev, model, lambda lat: rw, [3, 4, 5, 6], {"hps": 1.0, "pick": 0.5}, enc, pooled, tids,
+                                                       exchange=exchange, input_latents=lat0, noises=nzs)
+        res.append((stats.clone(), adv_t.clone(), gres["hps"].clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][1], res[1][1])
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-9), (res[0][0], res[1][0])
+    assert torch.allclose(res[0][2], res[1][2], rtol=1e-6)
+    for n, g0 in res[0][3].items():
+        assert ((res[1][3][n] - g0).norm() / g0.norm().clamp_min(1e-20)).item() < 1e-5, n
     # latency: fused exchange vs NCCL all_gather + advantage kernel (CUDA events, 200 calls each)
     mine_dev = {k: torch.randn(local_B, device=dev) for k in weights}
     def timed(fn, n=200):
