@@ -106,3 +106,41 @@ def test_product_never_imports_oracle():
     for f in (ROOT / "mixgrpo_b200").rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c_and_the_library_is_callable_from_c(tmp_path):
+    """include/mixgrpo_b200.h is valid C99 (no torch, no C++), and a C program can load the library and call it."""
+    import shutil
+    import subprocess
+    from mixgrpo_b200 import _build, _cabi
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    lib = _build.build()
+    src = tmp_path / "probe.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include "mixgrpo_b200.h"
+int main(int argc, char** argv) {
+  void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+  if (!h) { fprintf(stderr, "%s\n", dlerror()); return 2; }
+  int (*abi)(void) = (int (*)(void))dlsym(h, "mixgrpo_abi_version");
+  int64_t (*ws)(int64_t, int64_t) = (int64_t (*)(int64_t, int64_t))dlsym(h, "mixgrpo_step_workspace_bytes");
+  int64_t (*rb)(int, int64_t) = (int64_t (*)(int, int64_t))dlsym(h, "mixgrpo_peer_region_bytes");
+  int (*step)(const void*, int, const float*, int64_t, const void*, const float*, int64_t, float*, int64_t, float*, float*, float*, void*,
+              int64_t, int64_t, int64_t, const mixgrpo_step_coefs*, int, unsigned, void*) = dlsym(h, "mixgrpo_flow_step");
+  mixgrpo_step_coefs k = {0};
+  if (!abi || !ws || !rb || !step) return 3;
+  printf("%d %lld %lld %d\n", abi(), (long long)ws(12, 262144), (long long)rb(8, 36),
+         step(NULL, MIXGRPO_BF16, NULL, 0, NULL, NULL, 0, NULL, 0, NULL, NULL, NULL, NULL, 0, 1, 8, &k, MIXGRPO_SRC_NOISE, 0u, NULL));
+  return abi() == MIXGRPO_ABI_VERSION ? 0 : 4;
+}
+''')
+    exe = tmp_path / "probe"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic-errors", "-Wno-pedantic", "-I", str(ROOT / "include"), str(src), "-o", str(exe), "-ldl"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    abi, ws, rb, rc = r.stdout.split()
+    assert int(abi) == _cabi.ABI_VERSION and int(ws) == 256 and int(rb) == 256 + 2 * 8 * 36 * 8 + 2 * 8 * 256 * 8 and int(rc) == -1
