@@ -46,7 +46,8 @@ B, S, C = 12, 4096, 64          # group size, packed tokens (1024^2), channels
 N_STEPS, WINDOW, N_MODELS = 25, 4, 3
 ETA, SHIFT = 0.7, 3.0
 CLIP, ADV_CLIP, KL, GA = 1e-4, 5.0, 0.01, 3
-BYTES = {"ode": 10, "sde": 12, "sde_x0": 16, "train_fwd": 10, "bwd": 12, "sde_x0_philox": 14}   # SURVEY §8d, bf16 v/noise
+BYTES = {"ode": 10, "sde": 12, "sde_x0": 16, "train_fwd": 10, "bwd": 12, "sde_x0_philox": 14,   # SURVEY §8d, bf16 v/noise
+         "sde_x0_f32": 20, "dpm2_ode_x0": 18}                                                      # fp32 v/noise (configs[4]); Flash DPM-Solver++ order-2 ODE (configs[3])
 
 
 def algorithmic_bytes_per_step() -> int:
@@ -258,6 +259,10 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     sig = torch.linspace(1, 0, N_STEPS + 1)
     sig = (SHIFT * sig) / (1 + (SHIFT - 1) * sig)
     k, _ = coefs.flow(sig, 9, ETA, "ref_cuda", True)
+    k32, _ = coefs.flow(sig, 9, ETA, "ref_cuda", False)
+    kdpm, _ = coefs.dpm(sig, 12, 2, "dpmsolver++", "midpoint", "ref_cuda", True)
+    v32s = [torch.randn(B, S, C, device=dev, generator=g) for _ in range(ns)]
+    e32s = [torch.randn(B, S, C, device=dev, generator=g) for _ in range(ns)]
     e = B * S * C
 
     def run(kind, i):
@@ -271,12 +276,17 @@ def measure_roofline(dev, peak_gbs, peak_kind):
             ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_GIVEN, x_next=outs[(i + 1) % ns], out_logp=lps[i], want_x0=False, round_like_torch=True)
         elif kind == "bwd":
             ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True, out=gvs[i])
+        elif kind == "sde_x0_f32":         # fp32 model output and noise (configs[4]'s fp32 leg): 20 B/elem
+            ops.fused_step(ops.FLOW, v32s[i], xs[i], k32, src=SRC_NOISE, noise=e32s[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i])
+        elif kind == "dpm2_ode_x0":        # MixGRPO-Flash tail: DPM-Solver++ order-2 midpoint ODE step, previous x0 as the extra stream
+            ops.fused_step(ops.DPM, vs[i], xs[i], kdpm, src=SRC_DETERMINISTIC, m1=x0s[(i + 1) % ns], order=2, out_x_next=outs[i], out_logp=lps[i], want_x0=True,
+                           out_x0=x0s[i], round_like_torch=True)
         elif kind == "sde_x0_philox":      # noise drawn in the kernel: no noise tensor is read (and none was generated)
             ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_PHILOX, philox=(1234, 4 * i), out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], round_like_torch=True)
 
     res = {}
     s = torch.cuda.Stream(device=dev)
-    for kind in ("sde_x0", "sde", "ode", "train_fwd", "bwd", "sde_x0_philox"):
+    for kind in ("sde_x0", "sde", "ode", "train_fwd", "bwd", "sde_x0_philox", "sde_x0_f32", "dpm2_ode_x0"):
         with torch.cuda.stream(s):
             for i in range(ns):
                 run(kind, i)
