@@ -144,3 +144,21 @@ int main(int argc, char** argv) {
     assert r.returncode == 0, (r.stdout, r.stderr)
     abi, ws, rb, rc = r.stdout.split()
     assert int(abi) == _cabi.ABI_VERSION and int(ws) == 256 and int(rb) == 256 + 2 * 8 * 36 * 8 + 2 * 8 * 256 * 8 and int(rc) == -1
+
+
+def test_missing_library_fails_loudly_instead_of_falling_back(monkeypatch, tmp_path):
+    """No .so and no way to build it: loading raises (there is nothing else to route to)."""
+    from mixgrpo_b200 import _build, _cabi
+
+    def no_nvcc(*a, **k):
+        raise RuntimeError("mixgrpo_b200: nvcc not found; cannot build the CUDA library")
+
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_build, "LIB", tmp_path / "nope" / "libmixgrpo_b200.so")
+    monkeypatch.setattr(_build, "STAMP", tmp_path / "nope" / "libmixgrpo_b200.stamp")
+    monkeypatch.setattr(_build, "build", no_nvcc)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cabi.lib()
+    import mixgrpo_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mixgrpo_b200.load_library()
