@@ -220,5 +220,15 @@ def test_config0_train_one_step_composition():
                                                           input_latents=lat0, noises=[n for n in noises])
         assert samples_a["latents"].shape == samples["latents"].shape and torch.isfinite(stats_a).all()
         assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+        # ---- use_group False (TR:495-499): one pre-merged reward, global normalisation with the gathered statistics; no prompt repetition
+        args_g = _args(use_group=False, multi_reward_mix="reward_aggr")
+        merged = rewards["hps"] + 0.5 * rewards["pick"]
+        want_adv = GO.group_advantages(merged.cpu(), G, use_group=False, gathered=merged.cpu())
+        for exchange in (None, px):
+            model.zero_grad(set_to_none=True)
+            stats_g, gres, _, adv_g = trainer.train_one_step(args_g, DEV, model, lambda lat: merged, WINDOW, None, enc, pooled, text_ids, exchange=exchange,
+                                                             input_latents=lat0, noises=noises)
+            assert torch.allclose(adv_g.cpu(), want_adv, atol=1e-6) and torch.isfinite(stats_g).all()
+            assert torch.allclose(gres, merged.mean())
     finally:
         px.close()
