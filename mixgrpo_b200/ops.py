@@ -38,7 +38,28 @@ def _dtype_code(t: torch.Tensor, name: str) -> int:
 
 
 def _stream_ptr(device: torch.device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on ``device`` (torch._C._cuda_getCurrentRawStream: no Stream object)."""
+    idx = device.index
+    return torch._C._cuda_getCurrentRawStream(idx if idx is not None else torch.cuda.current_device())
+
+
+class _on_device:
+    """``with _on_device(dev)`` that costs nothing when ``dev`` is already current (the usual case: one process
+    per GPU) — the C ABI launches on the CURRENT device's context."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device: torch.device):
+        idx = device.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _rows(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
@@ -56,9 +77,9 @@ def _rows(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     return t, t.stride(0)
 
 
-def _workspace(device: torch.device, B: int, n: int) -> torch.Tensor:
+def _workspace(device: torch.device, B: int, n: int, stream: Optional[int] = None) -> torch.Tensor:
     need = _cabi.lib().mixgrpo_step_workspace_bytes(B, n)
-    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream if stream is not None else _stream_ptr(device))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)   # counters must start at zero
@@ -176,13 +197,13 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
             logp = out_logp
         else:
             logp = torch.empty((B,), dtype=torch.float32, device=dev)
-    ws = _workspace(dev, B, n) if want_logp else None
-    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
     st = _stream_ptr(dev)
+    ws = _workspace(dev, B, n, st) if want_logp else None
+    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
     common_out = (out_p, out_bs, x0.data_ptr() if want_x0 else None, mean.data_ptr() if want_mean else None,
                   logp.data_ptr() if want_logp else None, ws.data_ptr() if want_logp else None,
                   ws.numel() if want_logp else 0, B, n, C.byref(coefs))
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if family == FLOW:
             rc = lib.mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src, flags, st)
         elif family == DANCE:
@@ -219,7 +240,7 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
     if grad_v.dtype != v.dtype or grad_v.shape != v.shape or not grad_v.is_contiguous():
         raise ValueError("mixgrpo_b200: `out` must match model_output's dtype/shape and be contiguous")
     flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
-    with torch.cuda.device(v.device):
+    with _on_device(v.device):
         rc = lib.mixgrpo_logprob_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, g.data_ptr(),
                                      grad_v.data_ptr(), B, n, C.byref(coefs), flags, _stream_ptr(v.device))
     _cabi.check(rc, "logprob_bwd")
@@ -268,7 +289,7 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
     logp = out_logp if out_logp is not None else torch.empty((B,), dtype=torch.float32, device=dev)
     ws = _workspace(dev, B, n)
     flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = lib.mixgrpo_policy_fwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, logp.data_ptr(), ws.data_ptr(),
                                     ws.numel(), B, n, C.byref(coefs), C.byref(la), flags, _stream_ptr(dev))
     _cabi.check(rc, "policy_fwd")
@@ -298,7 +319,7 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     la, keep = _loss_args(old_logp, advantages, None, clip_range, adv_clip_max, kl_coeff, denom, B, dev)
     grad_v = torch.empty_like(v)
     flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early_loads else 0)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = lib.mixgrpo_policy_bwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, nl.data_ptr(), C.byref(la),
                                     grad_v.data_ptr(), B, n, C.byref(coefs), flags, _stream_ptr(dev))
     _cabi.check(rc, "policy_bwd")
@@ -329,7 +350,7 @@ def policy_step(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Ten
     grad_v = torch.empty_like(v)
     ws = _workspace(dev, B, n)
     flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = lib.mixgrpo_policy_step(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, logp.data_ptr(),
                                      grad_v.data_ptr(), ws.data_ptr(), ws.numel(), B, n, C.byref(coefs), C.byref(la), flags, _stream_ptr(dev))
     del keep
@@ -351,7 +372,7 @@ def cast_rows(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
     if dst.dtype != torch.float32 or dst.shape != src.shape or not dst[0].is_contiguous():
         raise ValueError("mixgrpo_b200: dst must be fp32, same shape, contiguous per sample")
     B, n = src.shape[0], src[0].numel()
-    with torch.cuda.device(src.device):
+    with _on_device(src.device):
         rc = _cabi.lib().mixgrpo_cast_rows(src.data_ptr(), code, dst.data_ptr(), dst.stride(0) if B > 1 else n, B, n, _stream_ptr(src.device))
     _cabi.check(rc, "cast_rows")
     launch_count += 1
@@ -384,7 +405,7 @@ def group_advantages(rewards: torch.Tensor, weights: Optional[torch.Tensor], num
     # every entry is written unless a ragged tail (local_B % G) exists, which the reference leaves at zero (TR:445)
     full = (not use_group) or (local_B % int(num_generations) == 0)
     adv = (torch.empty if full else torch.zeros)((local_B,), dtype=torch.float32, device=r.device)
-    with torch.cuda.device(r.device):
+    with _on_device(r.device):
         rc = lib.mixgrpo_group_advantages(r.data_ptr(), w_p, n_models, local_B, int(num_generations), int(trim_size),
                                           1 if use_group else 0, s_p, n_stat, adv.data_ptr(), _stream_ptr(r.device))
     _cabi.check(rc, "group_advantages")
@@ -413,7 +434,7 @@ def grpo_loss_fwd_bwd(new_logp: torch.Tensor, old_logp: torch.Tensor, advantages
         if stats_accum.dtype != torch.float32 or stats_accum.numel() != 4 or not stats_accum.is_contiguous():
             raise ValueError("mixgrpo_b200: stats_accum must be a contiguous fp32 [4] tensor")
         acc_p = stats_accum.data_ptr()
-    with torch.cuda.device(nl.device):
+    with _on_device(nl.device):
         rc = lib.mixgrpo_grpo_loss(nl.data_ptr(), ol.data_ptr(), ad.data_ptr(), B, float(clip_range), float(adv_clip_max),
                                    float(kl_coeff), float(denom), stats.data_ptr(), grad.data_ptr() if want_grad else None,
                                    acc_p, _stream_ptr(nl.device))
@@ -429,7 +450,7 @@ def pack_latents(latents: torch.Tensor, batch_size: int, num_channels: int, heig
     code = _dtype_code(latents, "latents")
     src = latents.contiguous().view(batch_size, num_channels, height, width)
     dst = torch.empty((batch_size, (height // 2) * (width // 2), num_channels * 4), dtype=latents.dtype, device=latents.device)
-    with torch.cuda.device(latents.device):
+    with _on_device(latents.device):
         rc = _cabi.lib().mixgrpo_pack_latents(src.data_ptr(), dst.data_ptr(), code, batch_size, num_channels, height, width,
                                               _stream_ptr(latents.device))
     _cabi.check(rc, "pack_latents")
@@ -449,7 +470,7 @@ def unpack_latents(latents: torch.Tensor, height: int, width: int, vae_scale_fac
     ww = 2 * (int(width) // (vae_scale_factor * 2))
     src = latents.contiguous()
     dst = torch.empty((b, ch // 4, hh, ww), dtype=latents.dtype, device=latents.device)
-    with torch.cuda.device(latents.device):
+    with _on_device(latents.device):
         rc = _cabi.lib().mixgrpo_unpack_latents(src.data_ptr(), dst.data_ptr(), code, b, ch // 4, hh, ww, float(divisor),
                                                 float(shift), _stream_ptr(latents.device))
     _cabi.check(rc, "unpack_latents")

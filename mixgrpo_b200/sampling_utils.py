@@ -48,6 +48,23 @@ def sd3_time_shift(shift, t):
     return (shift * t) / (1 + (shift - 1) * t)
 
 
+_scale_cache = {}
+
+
+def _scale_tensor(scale: float, device: torch.device) -> torch.Tensor:
+    """0-dim fp32 device tensor holding ``std_dev_t*sqrt(-dt)`` (the 5-tuple's last entry, SU:210), cached per (device,
+    value): 25 distinct values per schedule, so the steady state launches no fill kernel for an output no caller reads
+    (TR:149, SU:85,118).  Treat it as read-only."""
+    key = (device.type, device.index, scale)
+    t = _scale_cache.get(key)
+    if t is None:
+        if len(_scale_cache) > 4096:
+            _scale_cache.clear()
+        t = torch.full((), scale, dtype=torch.float32, device=device)
+        _scale_cache[key] = t
+    return t
+
+
 def _randn(shape, generator, device, dtype):
     """Noise source when the caller gives none (SU:189-194 ``randn_tensor``): torch's Philox on the
     target device.  A CPU generator draws on the CPU then moves, like diffusers' randn_tensor."""
@@ -108,7 +125,7 @@ def flow_grpo_step(
     k, scale = _coefs.flow(sigmas, index, eta, mode, bf16_v)
     rnd = bf16_v and mode != "fp32"
     # 5th output (SU:210): 0-dim device tensor like the reference; a plain float when the caller opted out
-    scale_t = torch.full((), scale, dtype=torch.float32, device=model_output.device) if return_mean else scale
+    scale_t = _scale_tensor(scale, model_output.device) if return_mean else scale
     if prev_sample is None:
         # rollout: the reference draws noise even when the step is deterministic (SU:188-195); only the
         # stochastic branch needs it here
