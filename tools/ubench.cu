@@ -111,7 +111,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 struct P {
   const __nv_bfloat16* v; const float* x; const __nv_bfloat16* e; float* xo; float* x0; float* logp; float* partials; unsigned* counters; unsigned long long* packed;
   long long n; int nblk; Coef c; CoefB cb;
+  int pf_dist, nsamp;      // MATH == 4: CTA (linear id L) bulk-prefetches the tile of CTA L + pf_dist into L2
 };
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // REDUCE: 0 none, 1 CTA partial + fence + ticket + last-CTA finalize, 2 CTA partial store only (finalize kernel separate),
 //         3 float RED into logp accumulator (no ticket)
@@ -134,7 +139,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_sde(const __grid_constant__ P p
     __syncthreads();
   }
   if constexpr (MATH >= 2) asm volatile("griddepcontrol.launch_dependents;");   // PDL: let the next grid start filling freed SMs
-  if constexpr (MATH == 2) asm volatile("griddepcontrol.wait;" ::: "memory");      // wait for the previous grid before ANY load
+  if constexpr (MATH == 2 || MATH == 4) asm volatile("griddepcontrol.wait;" ::: "memory");      // wait for the previous grid before ANY load
+  if constexpr (MATH == 4) {
+    // one thread pulls the inputs of the CTA that will run in this slot one wave later into L2 (3 bulk prefetches)
+    if (threadIdx.x == 0 && UNROLL == 1) {
+      const long long L = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.pf_dist;
+      const int by = (int)(L / gridDim.x), bx = (int)(L - (long long)by * gridDim.x);
+      if (by < p.nsamp) {
+        const long long off = (long long)bx * WORK * 8;
+        const long long rem = n - off;
+        if (rem > 0) {
+          const unsigned cnt = (unsigned)(rem < (long long)WORK * 8 ? rem : (long long)WORK * 8);
+          l2_prefetch_bulk(p.v + (long long)by * n + off, cnt * 2u);
+          l2_prefetch_bulk(p.x + (long long)by * n + off, cnt * 4u);
+          l2_prefetch_bulk(p.e + (long long)by * n + off, cnt * 2u);
+        }
+      }
+    }
+  }
   if constexpr (VEC == 8) {
     uint4 v[UNROLL], e[UNROLL];
     float x[UNROLL][8];
@@ -494,6 +516,7 @@ static int B = 12, S = 4096, NS = 10, REPS = 30;
 static long long n;
 static std::vector<Bufs> bufs;
 static float *d_logp, *d_partials; static unsigned* d_counters; static unsigned long long* d_packed;
+static int g_pf_dist = 888;
 static Coef coef = {0.8125f, 0.9937f, 1.0234f, -0.0262f, 0.1367f, 0.0372f, -1.99f, 0.9189f};
 static CoefB coefb = {0x3f503f50u, 0x3f833f83u, 0xbcd7bcd7u, 0x3e0c3e0cu};
 
@@ -527,7 +550,7 @@ static void run(const char* name) {
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
   int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, 0));
   auto launch = [&](int i, cudaStream_t st) {
-    P p{bufs[i].v, bufs[i].x, bufs[i].e, bufs[i].xo, bufs[i].x0, d_logp, d_partials, d_counters, d_packed, n, nblk, coef, coefb};
+    P p{bufs[i].v, bufs[i].x, bufs[i].e, bufs[i].xo, bufs[i].x0, d_logp, d_partials, d_counters, d_packed, n, nblk, coef, coefb, g_pf_dist, B};
     if (REDUCE == 3) cudaMemsetAsync(d_logp, 0, B * sizeof(float), st);
     if (MATH >= 2) {
       cudaLaunchConfig_t cfg = {};
@@ -575,6 +598,19 @@ int main(int argc, char** argv) {
     auto launch2 = [&](int i, cudaStream_t st) { k_copy<H_DEFAULT><<<(unsigned)((E / 8 + 255) / 256), 256, 0, st>>>(bufs[i].x, bufs[(i + 1) % NS].x, bufs[i].xo, bufs[i].x0, E); };
     us = time_graph(launch2, NS, REPS);
     printf("%-34s %7.2f us  %7.1f GB/s  %.3f\n", "copy2x default hints", us, E * 16 / us / 1e3, E * 16 / us / 1e3 / 6533.5);
+  }
+  if (argc > 3 && !strcmp(argv[3], "pf")) {
+    // L2 prefetch of the NEXT wave's inputs (cp.async.bulk.prefetch.L2), distance in CTAs
+    run<8, 1, H_NC_NA, 7, 256, 6, 2>("packed + PDL (shipped)");
+    for (int d : {888, 740, 592, 444, 296, 148, 1036, 1184}) {
+      g_pf_dist = d;
+      char nm[64]; snprintf(nm, sizeof nm, "+ L2 bulk prefetch, dist %d", d);
+      run<8, 1, H_NC_NA, 7, 256, 6, 4>(nm);
+    }
+    g_pf_dist = 888;
+    run<8, 1, H_NC_NA, 0, 256, 6, 4>("prefetch 888, no reduction");
+    run<8, 1, H_NC_NA, 7, 192, 8, 4>("prefetch 888, b192 c8");
+    return 0;
   }
   if (argc > 3 && !strcmp(argv[3], "wave")) {
     // one-wave shapes at (12,4096,64): every load of the launch is issued before the first CTA retires
