@@ -160,7 +160,7 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
                    reward_weights, encoder_hidden_states, pooled_prompt_embeds, text_ids, *, exchange=None,
                    on_accumulated: Optional[Callable[[int], None]] = None, micro_batch: int = 1,
                    input_latents: Optional[torch.Tensor] = None, noises=None, generator: Optional[torch.Generator] = None,
-                   rng=None):
+                   rng=None, split_groups: bool = False):
     """The hot path of the reference's ``train_one_step`` (TR:341-640) as one call: prompt repetition (TR:369-384), batched
     rollout (TR:386-399), sample bookkeeping (TR:400-415), reward exchange + group-relative advantages (TR:417-501), step
     permutation / positive-negative re-ranging (TR:503-535), the (sample, window step) policy-update loop (TR:536-615) and
@@ -170,12 +170,19 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
 
     ``exchange``: a :class:`mixgrpo_b200.peer.PeerExchange` — reward gather + advantages and the logging all-reduce then
     run as one fused NVLink kernel each; without it NCCL (or nothing, single process) is used.
+    ``split_groups`` (SURVEY §8e extended mode): a prompt group is spread over several ranks — ``num_generations`` counts the
+    samples of a group across ranks, consecutive in rank-major order, and the statistics come from the gathered rewards;
+    each rank repeats its prompt ``num_generations // world`` times.
     Returns ``(stats [4] = total_loss, policy_total_loss, kl_total_loss, total_clip_frac — rank-averaged device tensor,
     gathered_reward_res (per-model mean of the gathered rewards, device tensors), samples, advantages)``; nothing syncs the
     host except the optional ``advantage_rerange_strategy`` (which needs the advantages' signs, like the reference)."""
     G = int(args.num_generations)
+    world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+    local_G = G // world if split_groups else G
+    if split_groups and (G % world != 0 or not getattr(args, "use_group", True)):
+        raise ValueError("split_groups needs use_group and num_generations divisible by the world size")
     if getattr(args, "use_group", True):                                             # TR:369-384
-        rep = lambda t: None if t is None else torch.repeat_interleave(t, G, dim=0)   # noqa: E731
+        rep = lambda t: None if t is None else torch.repeat_interleave(t, local_G, dim=0)   # noqa: E731
         encoder_hidden_states, pooled_prompt_embeds, text_ids = rep(encoder_hidden_states), rep(pooled_prompt_embeds), rep(text_ids)
     rewards, all_latents, all_log_probs, sigma_schedule, image_ids = sample_reference_model(
         args, device, transformer, encoder_hidden_states, pooled_prompt_embeds, text_ids, decode_and_score, timesteps_train,
@@ -186,7 +193,10 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
     trimmed = float(getattr(args, "trimmed_ratio", 0.0) or 0.0)
     if exchange is not None:                                                         # TR:417-501 in ONE launch
         advantages, gathered = exchange.gather_advantages(rewards, G, reward_weights, trimmed_ratio=trimmed,
-                                                          mode="local" if use_group else "global")
+                                                          mode=("split" if split_groups else "local") if use_group else "global")
+    elif split_groups:
+        gathered = _grpo.gather_rewards(rewards)
+        advantages = _grpo.compute_group_advantages_split(rewards, G, reward_weights, trimmed_ratio=trimmed)
     else:
         gathered = _grpo.gather_rewards(rewards)
         advantages = _grpo.compute_group_advantages(rewards, G, reward_weights, trimmed_ratio=trimmed, use_group=use_group,

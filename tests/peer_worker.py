@@ -107,6 +107,19 @@ def main():
     assert torch.allclose(res[0][2], res[1][2], rtol=1e-6)
     for n, g0 in res[0][3].items():
         assert ((res[1][3][n] - g0).norm() / g0.norm().clamp_min(1e-20)).item() < 1e-5, n
+    # extended mode: ONE group of 4*world samples spread over the ranks (4 each): statistics from the gathered rewards
+    targs.num_generations = 4 * world
+    adv_split = []
+    for exchange in (None, px):
+        model.zero_grad(set_to_none=True)
+        _, _, _, adv_t = trainer.train_one_step(targs, dev, model, lambda lat: rw, [3, 4, 5, 6], {"hps": 1.0, "pick": 0.5}, enc, pooled, tids,
+                                                exchange=exchange, input_latents=lat0, noises=nzs, split_groups=True)
+        adv_split.append(adv_t.clone())
+    all_rw = [None] * world
+    dist.all_gather_object(all_rw, {k: v.cpu() for k, v in rw.items()})
+    full = GO.group_advantages({k: torch.cat([r[k] for r in all_rw]) for k in rw}, 4 * world, {"hps": 1.0, "pick": 0.5})
+    assert torch.equal(adv_split[0], adv_split[1])
+    assert torch.allclose(adv_split[1].cpu(), full[rank * 4:(rank + 1) * 4], rtol=0, atol=1e-6)
     # latency: fused exchange vs NCCL all_gather + advantage kernel (CUDA events, 200 calls each)
     mine_dev = {k: torch.randn(local_B, device=dev) for k in weights}
     def timed(fn, n=200):
