@@ -70,7 +70,8 @@ def _weights_on(device: torch.device, w: Tuple[float, ...]) -> torch.Tensor:
     t = _weight_cache.get(key)
     if t is None:
         t = torch.tensor(w, dtype=torch.float32).to(device)
-        _weight_cache[key] = t
+        if not torch.cuda.is_current_stream_capturing():                   # a copy recorded into a CUDA graph only runs on replay
+            _weight_cache[key] = t
     return t
 
 

@@ -83,7 +83,10 @@ def _workspace(device: torch.device, B: int, n: int, stream: Optional[int] = Non
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)   # counters must start at zero
-        _workspaces[key] = ws
+        if not torch.cuda.is_current_stream_capturing():
+            _workspaces[key] = ws
+        # else: allocated inside a CUDA-graph capture (no eager warm-up on this stream) — the zero fill is part of the graph
+        # and the memory belongs to the graph's pool, so it must not be handed to later eager calls
     return ws
 
 

@@ -58,6 +58,9 @@ def _scale_tensor(scale: float, device: torch.device) -> torch.Tensor:
     key = (device.type, device.index, scale)
     t = _scale_cache.get(key)
     if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            # a fill recorded into a CUDA graph only runs on replay and its memory belongs to the graph's pool: never cache it
+            return torch.full((), scale, dtype=torch.float32, device=device)
         if len(_scale_cache) > 4096:
             _scale_cache.clear()
         t = torch.full((), scale, dtype=torch.float32, device=device)

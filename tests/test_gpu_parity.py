@@ -647,3 +647,41 @@ def test_full_size_dance_and_flash_dpm_vs_reference_ops_on_device(dtype):
         assert _rel(out[0], ref[0]) < 1e-5, f"x_next step {idx}"
         assert st.lower_order_nums == oh.lower_order_nums
         xs = ref[0]
+
+
+def test_capture_without_warmup_does_not_poison_later_eager_calls():
+    """Module-level caches (log-prob workspace, the 0-dim scale tensor, reward weights) must never keep tensors that were
+    created INSIDE a CUDA-graph capture: their fills only run on replay and their memory belongs to the graph's pool."""
+    import gc
+    from mixgrpo_b200 import grpo, sampling_utils as su
+    d = _dev()
+    x, v, eps, _ = _inputs(3, 96, torch.bfloat16, seed=91)
+    x, v, eps = x.to(d), v.to(d), eps.to(d)
+    idx = 17                                                     # a step no other test's scale cache has seen at this eta
+    eta = 0.65
+    want = O.flow_step(v.cpu(), x.cpu(), eta, SIG, idx, None, eps.cpu(), False)
+    rewards = {"a": torch.tensor([0.3, -1.0, 2.0], device=d), "b": torch.tensor([1.0, 0.5, -0.25], device=d)}
+    wts = {"a": 0.37, "b": 1.91}                                 # a weight tuple nobody cached
+    want_adv = GO.group_advantages({k: t.cpu() for k, t in rewards.items()}, 3, wts)
+    s = torch.cuda.Stream()                                      # fresh stream: no workspace exists for it yet
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = su.flow_grpo_step(v, x, eta, SIG, idx, None, noise=eps, rounding="ref_cpu")
+        for _ in range(2):
+            g.replay()
+        s.synchronize()
+        assert torch.equal(out[0].cpu(), want[0]) and torch.allclose(out[2].cpu(), want[2], rtol=1e-5, atol=0)
+        assert abs(float(out[4]) - float(want[4])) < 1e-7
+        del g, out
+        gc.collect()
+        torch.cuda.empty_cache()
+        scratch = [torch.full((1 << 18,), float("nan"), device=d) for _ in range(8)]   # recycle whatever the graph's pool released
+        again = su.flow_grpo_step(v, x, eta, SIG, idx, None, noise=eps, rounding="ref_cpu")
+        adv = grpo.compute_group_advantages(rewards, 3, wts)
+        s.synchronize()
+        del scratch
+    assert torch.equal(again[0].cpu(), want[0]) and torch.allclose(again[2].cpu(), want[2], rtol=1e-5, atol=0)
+    assert abs(float(again[4]) - float(want[4])) < 1e-7
+    assert torch.allclose(adv.cpu(), want_adv, atol=1e-6)
