@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(e, he.data(), E * 2, cudaMemcpyHostToDevice));
   cudaStream_t st; CK(cudaStreamCreate(&st));
   const int rc = mixgrpo_flow_step(v, MIXGRPO_BF16, x, n, e, nullptr, n, xn, n, x0, nullptr, lp, ws, wsb, B, n, &k, MIXGRPO_SRC_NOISE,
-                                   MIXGRPO_FLAG_ROUND_LIKE_TORCH, st);
+                                   MIXGRPO_FLAG_ROUND_LIKE_TORCH, st, nullptr);
   if (rc != 0) { fprintf(stderr, "mixgrpo_flow_step: %d (%s)\n", rc, mixgrpo_error_string(rc)); return 3; }
   CK(cudaStreamSynchronize(st));
   std::vector<float> hlp(B), hxn(E), hx0(E);

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MIXGRPO_ABI_VERSION 3
+#define MIXGRPO_ABI_VERSION 4
 
 /* element type of model_output / noise / grad_model_output */
 enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
@@ -49,13 +49,23 @@ enum {
 typedef struct mixgrpo_philox_args {
   uint64_t seed;
   uint64_t offset;
+  /* CUDA-graph-safe state (nullable): DEVICE pointer to {seed, base offset}.  When set, the kernel reads both from
+   * device memory at run time — seed = device_state[0], offset = device_state[1] + `offset` (the host-known position
+   * inside the graph) — so replays of a captured launch draw fresh noise once mixgrpo_philox_advance has moved the base
+   * (torch's graph-safe generator does the same with its seed / offset-extragraph pointers).  `seed` is then ignored. */
+  const uint64_t* device_state;
 } mixgrpo_philox_args;
 
 /* flags */
 #define MIXGRPO_FLAG_ROUND_LIKE_TORCH 1u /* reproduce torch's bf16 type-promotion roundings */
-#define MIXGRPO_FLAG_PDL_EARLY_LOADS  2u /* backward only: v / x / x_next were NOT written by the kernel launched
-                                            immediately before on this stream (e.g. right after mixgrpo_policy_fwd):
-                                            their loads may overlap that kernel's tail (programmatic dependent launch) */
+#define MIXGRPO_FLAG_PDL_EARLY_LOADS  2u /* NONE of the streamed inputs (v / x / x_next / noise / history) was written by
+                                            the kernel launched immediately before on this stream (e.g. a backward right
+                                            after mixgrpo_policy_fwd, which only writes [B] log-probs): their loads are
+                                            issued before griddepcontrol.wait and overlap that kernel's tail */
+#define MIXGRPO_FLAG_PDL_EARLY_V      4u /* step kernels: model_output and noise were not written by the immediately
+                                            preceding launch (they come from the DiT / randn, several launches back) but
+                                            the latents may have been (step i reads what step i-1 wrote): only v / noise
+                                            are loaded before the wait */
 
 /* error codes */
 #define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
@@ -87,6 +97,7 @@ typedef struct mixgrpo_philox_args {
  *    5..8   mean   = c5*x + c6*D0 + c7*D1 + c8*D2                (signs folded into the coefficients)
  *    9..12  x_ode  = c9*x + c10*D0 + c11*D1 + c12*D2
  *    13 scale = sigma_t*sqrt(1-exp(-2h))  (noise factor)
+ *    14 sigma_s as the log-prob backward multiplies by it (mixgrpo_logprob_bwd family 2)
  */
 typedef struct mixgrpo_step_coefs {
   float two_var;
@@ -95,9 +106,10 @@ typedef struct mixgrpo_step_coefs {
   float c[16];
 } mixgrpo_step_coefs;
 
-/* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 16-byte record per
- * sample — a 64-bit packed accumulator ([fixed-point sum | poison | arrival count], csrc/step_kernels.cu) for the
- * deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu).  The layout does
+/* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 32-byte record per
+ * sample — a 64-bit packed accumulator ([fixed-point sum | wide-share count | arrival count], csrc/step_kernels.cu) for
+ * the deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu), and a 64-bit side
+ * accumulator for shares too large for the packed field (csrc/step_math.cuh).  The layout does
  * not depend on B and kernels leave the accumulators zeroed again, so one allocation can be reused by successive
  * launches of any batch size on the same stream (never by launches that may run concurrently). */
 int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
@@ -129,33 +141,54 @@ const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGe
  *   logp_out        fp32 [B] or NULL
  *   workspace       >= mixgrpo_step_workspace_bytes(B,n), zeroed once at allocation
  */
+/* Optional second output of a step launch (nullable `ext`): the latents handed to the VAE, i.e. what the reference
+ * computes after the rollout with two more passes over the final latent — unpack_latents (TR:102-115) then
+ * `latents / 0.3611 + 0.1159` (TR:286-287).  The rollout's LAST step writes it straight from its registers:
+ *   decode_out[b][c][2hp+dh][2wp+dw] = src[b][hp*(W/2)+wp][c*4+dh*2+dw] / divisor + shift,   n == C*H*W
+ * with src = x_next (from_x0 == 0; TR:150-152 `latents = z`) or x0 (from_x0 != 0; --drop_last_sample, SU:149-150).
+ * fp32 out, (B,C,H,W) contiguous, H and W even; needs the vector path (n % 8 == 0, aligned pointers), C % 2 == 0. */
+typedef struct mixgrpo_step_ext {
+  float* decode_out;
+  int C, H, W;
+  float divisor, shift;
+  int from_x0;
+  int reciprocal;   /* 0: true division (what torch computes on CPU tensors); 1: src * (1.0f / divisor), which is what torch's CUDA
+                       div-by-python-scalar kernel computes (one rounding more; differs from true division by <= 1 ulp) */
+} mixgrpo_step_ext;
+
 int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
                       const void* noise, const float* x_next_in, int64_t in_bs,
                       float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
                       float* logp_out, void* workspace, int64_t workspace_bytes,
                       int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                      int src, unsigned flags, void* stream);
+                      int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext);
 
 int mixgrpo_dance_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
                        const float* noise, const float* x_next_in, int64_t in_bs,
                        float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
                        float* logp_out, void* workspace, int64_t workspace_bytes,
                        int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                       int src, int sde_solver, unsigned flags, void* stream);
+                       int src, int sde_solver, unsigned flags, void* stream, const mixgrpo_step_ext* ext);
 
 int mixgrpo_dpm_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
                      const float* noise, const float* m1, const float* m2, int order,
                      float* x_next_out, int64_t out_bs, float* x0_out, float* mean_out,
                      float* logp_out, void* workspace, int64_t workspace_bytes,
                      int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                     int src, unsigned flags, void* stream);
+                     int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext);
+
+/* Moves a graph-safe Philox state's base offset: device_state[1] += increment (one tiny launch, stream-ordered after the
+ * step launches that consumed the numbers; issue it once per rollout, captured in the same graph). */
+int mixgrpo_philox_advance(uint64_t* device_state, uint64_t increment, void* stream);
 
 /* ---- backward of the transition log-prob w.r.t. model_output ----------------------------------
  * Replaces autograd through SU:175-208 / SU:224-250 when TR:585 calls loss.backward():
  *   grad_v = dL/dlogp[b] * (x_next - mean)/scale^2 * dmean/dv / n      (closed form)
  * mean is recomputed from (v, x) in the same pass; grad_logp is a DEVICE vector [B], so no host
  * sync sits between the loss kernel and this one.  grad_v has dtype v_dtype.
- * family: 0 flow, 1 dance (sde_solver=True, the only trained variant TR:159-168). */
+ * family: 0 flow, 1 dance (sde_solver=True, the only trained variant TR:159-168), 2 dpm order 1 (the
+ * dpm_apply_strategy == "all" training call, TR:169-180: dpm_state=None, so always the first-order update;
+ * x_next is the sample that forward call drew; coefs from the same dpm table, c[0] sigma_s, c[6] the x0 coefficient). */
 int mixgrpo_logprob_bwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
                         const float* x_next, int64_t in_bs, const float* grad_logp,
                         void* grad_v, int64_t B, int64_t n,
@@ -187,6 +220,35 @@ int mixgrpo_policy_bwd(int family, const void* v, int v_dtype, const float* x, i
                        const float* x_next, int64_t in_bs, const float* new_logp,
                        const mixgrpo_loss_args* loss, void* grad_v, int64_t B, int64_t n,
                        const mixgrpo_step_coefs* coefs_host, unsigned flags, void* stream);
+
+/* ---- the window's policy updates batched: ONE forward launch and ONE backward launch for n_items (<= 8) independent
+ * (batch, window step) updates — the 4 SDE-window steps of TR:536-585 are independent of one another given their model
+ * outputs, so their log-prob + loss forwards share a launch (grid.y = n_items * B: 126 MB instead of 4 x 31 MB at group
+ * 12, where a 31 MB launch is ~2 us of ramp/drain on 5 us of streaming) and so do their backwards.  Item j has its own
+ * tensors, per-step scalar block, old log-probs and stats rows; advantages [B] and the loss scalars are shared.  Results
+ * are bit-identical to n_items calls of mixgrpo_policy_fwd / mixgrpo_policy_bwd.  workspace >=
+ * mixgrpo_step_workspace_bytes(n_items * B, n).  Ragged / unaligned tensors return MIXGRPO_EUNSUPPORTED (nothing
+ * launched): call the single-item entry points then. */
+#define MIXGRPO_POLICY_MAX_ITEMS 8
+typedef struct mixgrpo_policy_item {
+  const void* v;             /* model output (B,n), dtype v_dtype, contiguous */
+  const float* x;            /* latents before the step, batch stride x_bs */
+  const float* x_next;       /* stored latents after the step, batch stride in_bs */
+  int64_t x_bs, in_bs;
+  float* logp;               /* [B]: written by _fwd_multi, read by _bwd_multi (the new log-probs) */
+  const float* old_logp;     /* [B] */
+  float* stats_rows;         /* [B,4] or NULL (forward) */
+  void* grad_v;              /* (B,n) dtype v_dtype (backward) */
+  mixgrpo_step_coefs coefs;  /* this step's scalar block */
+} mixgrpo_policy_item;
+
+int mixgrpo_policy_fwd_multi(int family, int v_dtype, const mixgrpo_policy_item* items_host, int n_items,
+                             const float* advantages, double clip_range, double adv_clip_max, double kl_coeff,
+                             double denom, int accumulate, void* workspace, int64_t workspace_bytes, int64_t B,
+                             int64_t n, unsigned flags, void* stream);
+int mixgrpo_policy_bwd_multi(int family, int v_dtype, const mixgrpo_policy_item* items_host, int n_items,
+                             const float* advantages, double clip_range, double adv_clip_max, double kl_coeff,
+                             double denom, int64_t B, int64_t n, unsigned flags, void* stream);
 
 /* ---- single-pass policy update: log-prob forward + loss + log-prob backward in ONE launch, 12 B/elem ----------
  * Same inputs, outputs and bits as mixgrpo_policy_fwd followed by mixgrpo_policy_bwd (new log-probs [B], stats rows,

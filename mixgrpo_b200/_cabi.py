@@ -15,10 +15,12 @@ F32, BF16 = 0, 1
 SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC, SRC_PHILOX = 0, 1, 2, 3
 FLAG_ROUND_LIKE_TORCH = 1
 FLAG_PDL_EARLY_LOADS = 2
+FLAG_PDL_EARLY_V = 4
+POLICY_MAX_ITEMS = 8
 ADV_GROUP_LOCAL, ADV_GROUP_SPLIT, ADV_GLOBAL = 0, 1, 2
 EUNSUPPORTED = -4
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class StepCoefs(C.Structure):
@@ -28,7 +30,13 @@ class StepCoefs(C.Structure):
 
 class PhiloxArgs(C.Structure):
     """mirror of ``mixgrpo_philox_args`` (include/mixgrpo_b200.h)."""
-    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64)]
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("device_state", C.c_void_p)]
+
+
+class StepExt(C.Structure):
+    """mirror of ``mixgrpo_step_ext`` (include/mixgrpo_b200.h): the decode-ready second output of a step launch."""
+    _fields_ = [("decode_out", C.c_void_p), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("divisor", C.c_float),
+                ("shift", C.c_float), ("from_x0", C.c_int), ("reciprocal", C.c_int)]
 
 
 class LossArgs(C.Structure):
@@ -38,9 +46,18 @@ class LossArgs(C.Structure):
                 ("accumulate", C.c_int)]
 
 
+class PolicyItem(C.Structure):
+    """mirror of ``mixgrpo_policy_item`` (include/mixgrpo_b200.h)."""
+    _fields_ = [("v", C.c_void_p), ("x", C.c_void_p), ("x_next", C.c_void_p), ("x_bs", C.c_int64), ("in_bs", C.c_int64),
+                ("logp", C.c_void_p), ("old_logp", C.c_void_p), ("stats_rows", C.c_void_p), ("grad_v", C.c_void_p),
+                ("coefs", StepCoefs)]
+
+
 _P, _I64, _I, _U, _F, _D = C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_float, C.c_double
 _CP = C.POINTER(StepCoefs)
 _LP = C.POINTER(LossArgs)
+_XP = C.POINTER(StepExt)
+_IP = C.POINTER(PolicyItem)
 
 # name -> (restype, argtypes); every symbol include/mixgrpo_b200.h declares
 SIGNATURES = {
@@ -49,12 +66,15 @@ SIGNATURES = {
     "mixgrpo_build_info": (C.c_char_p, []),
     "mixgrpo_set_tuning": (_I, [_I, _I]),
     "mixgrpo_error_string": (C.c_char_p, [_I]),
-    "mixgrpo_flow_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P]),
-    "mixgrpo_dance_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _I, _U, _P]),
-    "mixgrpo_dpm_step": (_I, [_P, _I, _P, _I64, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P]),
+    "mixgrpo_flow_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P, _XP]),
+    "mixgrpo_dance_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _I, _U, _P, _XP]),
+    "mixgrpo_dpm_step": (_I, [_P, _I, _P, _I64, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P, _XP]),
+    "mixgrpo_philox_advance": (_I, [_P, C.c_uint64, _P]),
     "mixgrpo_logprob_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _CP, _U, _P]),
     "mixgrpo_policy_fwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),
     "mixgrpo_policy_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _LP, _P, _I64, _I64, _CP, _U, _P]),
+    "mixgrpo_policy_fwd_multi": (_I, [_I, _I, _IP, _I, _P, _D, _D, _D, _D, _I, _P, _I64, _I64, _I64, _U, _P]),
+    "mixgrpo_policy_bwd_multi": (_I, [_I, _I, _IP, _I, _P, _D, _D, _D, _D, _I64, _I64, _U, _P]),
     "mixgrpo_policy_step": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),
     "mixgrpo_cast_rows": (_I, [_P, _I, _P, _I64, _I64, _I64, _P]),
     "mixgrpo_group_advantages": (_I, [_P, _P, _I, _I64, _I, _I, _I, _P, _I64, _P, _P]),

@@ -213,8 +213,11 @@ def dpm(sigmas: torch.Tensor, index: int, order: int, algo: str, solver_type: st
     scale = sg_t * dt_sqrt                                                # SU:434 std_dev_t * dt_sqrt
     emulate = bf16_v and mode != "fp32"
     sig_x0 = _bf(sg_0) if emulate else sg_0                               # SU:394 sigma_t * model_output
+    # the same factor as autograd's mul backward sees it (`grad * sigma`: sigma is then the RIGHT operand, which torch
+    # keeps in fp32 on CPU and casts to bf16 on CUDA) — c[14], read by the order-1 log-prob backward only
+    sig_bwd = _bf(sg_0) if (emulate and mode == "ref_cuda") else sg_0
     k = _pack(2 * (scale ** 2), torch.log(scale), _log_norm(),
-              [sig_x0, k1, k2, k3, k4, *m, *o, scale])
+              [sig_x0, k1, k2, k3, k4, *m, *o, scale, sig_bwd])
     out = (k, float(scale))
     _remember(key, out)
     return out

@@ -64,6 +64,20 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
     round_like_torch<RND>(g);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] = __fmul_rn(g[i], c[2]);
+  } else if constexpr (FAM == 2) {   // dpm order 1 (TR:169-180: dpm_state=None): mean = c5*x + c6*x0, x0 = x - sigma_s*v (SU:394, SU:426-444)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(c[0], v[i]);
+    round_like_torch<RND>(t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      x0[i] = __fsub_rn(x[i], t[i]);
+      mu[i] = __fadd_rn(__fmul_rn(c[5], x[i]), __fmul_rn(c[6], x0[i]));
+      const float gm = __fmul_rn(gs, __fmul_rn(2.f, __fsub_rn(xn[i], mu[i])));
+      g[i] = -__fmul_rn(gm, c[6]);                  // d/dx0 through the (sign-folded) coefficient, then x0 = x - t
+    }
+    round_like_torch<RND>(g);                       // grad of the bf16 product t = sigma_s*v
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = __fmul_rn(g[i], c[14]);   // c[14]: sigma_s as autograd's `grad * other` sees it
   } else {                    // dance with sde_solver=True, SU:224-234
 #pragma unroll
     for (int i = 0; i < VEC; ++i) t[i] = __fmul_rn(c[0], v[i]);
@@ -125,7 +139,7 @@ static int logprob_bwd_impl(int family, const void* v, int v_dtype, const float*
                             const mixgrpo_step_coefs* coefs_host, const mixgrpo_loss_args* loss, unsigned flags, void* stream) {
   if (!v || !x || !x_next || !grad_logp || !grad_v || !coefs_host || B <= 0 || B > 65535 || n <= 0) return MIXGRPO_EINVAL;
   if (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) return MIXGRPO_EINVAL;
-  if (family != 0 && family != 1) return MIXGRPO_EINVAL;
+  if (family < 0 || family > 2 || (family == 2 && loss)) return MIXGRPO_EINVAL;
   BwdParams p;
   p.v = v; p.x = x; p.x_next = x_next; p.grad_logp = grad_logp; p.grad_v = grad_v;
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.k = *coefs_host;
@@ -138,6 +152,7 @@ static int logprob_bwd_impl(int family, const void* v, int v_dtype, const float*
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool early = (flags & MIXGRPO_FLAG_PDL_EARLY_LOADS) != 0;
+  if (family == 2) return bwd_family<2>(p, v_dtype, B, vec, rnd, early, st);
   return family == 0 ? bwd_family<0>(p, v_dtype, B, vec, rnd, early, st) : bwd_family<1>(p, v_dtype, B, vec, rnd, early, st);
 }
 

@@ -124,7 +124,7 @@ __device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned lo
 // the immediately preceding kernel does not write, MIXGRPO_FLAG_PDL_EARLY_LOADS) safe.  After a non-PDL kernel (torch,
 // cuBLAS) the attribute is inert and ordering is the ordinary stream order.  Measured: -0.4 us per chained launch,
 // -1.1 us with early loads (profiles/r01_design_space.md).
-extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_kernels.cu
+extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_flow.cu
 }  // namespace mg
 int mixgrpo_peer_set_timeout_ms(int ms);   // mixgrpo_set_tuning key 2, defined in peer_kernels.cu
 int mixgrpo_policy_set_tuning(int key, int value);   // keys 3-5, defined in policy_kernels.cu

@@ -29,7 +29,7 @@ struct PolicyStepParams {
   const float* x_next;
   void* grad_v;
   float* logp_out;
-  unsigned long long* acc;     // workspace records, 16 B per sample: acc[kWsStride*b] = packed accumulator (as the step kernels use it)
+  unsigned long long* acc;     // workspace records, 32 B per sample: acc[kWsStride*b] = packed accumulator (as the step kernels use it)
   uint32_t* epoch;             // epoch[2*kWsStride*b]: bumped once per launch per sample by the sample's finalizer
   uint32_t* status;            // set to 1 when a wait timed out
   long long n, x_bs, in_bs, T; // T = B * tps tiles in total
@@ -153,16 +153,12 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
     const float* w = s_part + tid * (kThreads / 32);
     // the order of mg::step_kernel's second-stage xor-shuffle tree over the 8 warp sums
     const float t = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[4]), __fadd_rn(w[2], w[6])), __fadd_rn(__fadd_rn(w[1], w[5]), __fadd_rn(w[3], w[7])));
-    float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
-    const float cap = 255.0f / (float)p.tps;
-    unsigned long long add = 1ull;
-    if (!(r >= 0.f && r <= cap)) { add += 1ull << kCountBits; r = 0.f; }
-    add += __float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits);
-    const unsigned long long old = atomicAdd(&p.acc[kWsStride * my_b], add);
+    const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
+    unsigned long long* rec = p.acc + kWsStride * my_b;
+    const unsigned long long add = packed_share(r, p.tps, rec);
+    const unsigned long long old = atomicAdd(rec, add);
     if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(p.tps - 1)) {
-      const unsigned long long tot = old + add;
-      float q = (float)((double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0));
-      if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) q = __int_as_float(0x7fc00000);
+      const float q = packed_total(old + add, rec);
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);      // SU:201-208
       p.logp_out[my_b] = lp;
       p.acc[kWsStride * my_b] = 0ull;

@@ -1,0 +1,98 @@
+// flow_grpo_step family (SU:157-210) of the fused step kernel + the entry points that do not belong to one family.
+#include "step_kernel.cuh"
+
+namespace mg {
+int g_max_ctas_per_sample = kMaxCtasPerSample;          // bench knob (mixgrpo_set_tuning key 0)
+int g_use_pdl = 1;                                      // bench knob (key 1): programmatic dependent launch on/off
+int policy_fwd_dance(StepParams& p, int v_dtype, int64_t B, bool vec, bool rnd, cudaStream_t st);   // step_dance.cu
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n) {
+  if (B <= 0 || n <= 0) return 0;
+  // one 32-byte record per sample: { packed 64-bit accumulator | 32-bit epoch | 32-bit status (record 0) | 64-bit side
+  // accumulator for oversized shares | pad } — the layout does not depend on B, so calls with different batch sizes can
+  // share one zero-initialised allocation
+  return ((B * (int64_t)(kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
+  if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
+  if (key >= 3 && key <= 5) return mixgrpo_policy_set_tuning(key, value);
+  if (key == 1) {
+    if (value != 0 && value != 1) return MIXGRPO_EINVAL;
+    const int old = g_use_pdl;
+    g_use_pdl = value;
+    return old;
+  }
+  if (key != 0 || value < 1 || value > kMaxCtasPerSample) return MIXGRPO_EINVAL;
+  const int old = g_max_ctas_per_sample;
+  g_max_ctas_per_sample = value;
+  return old;
+}
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs, const void* noise,
+                                 const float* x_next_in, int64_t in_bs, float* x_next_out, int64_t out_bs,
+                                 float* x0_out, float* mean_out, float* logp_out, void* workspace,
+                                 int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
+                                 int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext) {
+  int err = 0;
+  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
+  if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
+  StepParams p;
+  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
+  if (src == MIXGRPO_SRC_PHILOX) set_philox(p, noise);
+  set_early(p, flags);
+  const bool vec = vector_ok(p, v_dtype, v_dtype, n);
+  if ((err = set_ext(p, ext, n, vec, src)) != 0) return err;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
+  if (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, true, false>(p, B, src, vec, st);
+  return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, false, false>(p, B, src, vec, st);
+}
+
+// Fused policy-update forward: log p(x_next | x, v) for the stored transition (TR:149-168 via grpo_one_step) AND the
+// per-sample clipped-ratio loss terms (TR:560-583) accumulated into stats_rows — one launch, nothing else.
+extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
+                                  const float* x_next, int64_t in_bs, float* logp_out, void* workspace, int64_t workspace_bytes,
+                                  int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, const mixgrpo_loss_args* loss,
+                                  unsigned flags, void* stream) {
+  int err = 0;
+  if (!coefs_host || !logp_out || !x_next || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err))
+    return err ? err : MIXGRPO_EINVAL;
+  if (family != kFlow && family != kDance) return MIXGRPO_EINVAL;
+  if (loss && (!loss->old_logp || !loss->advantages)) return MIXGRPO_EINVAL;
+  StepParams p;
+  fill(p, v, x, x_bs, nullptr, x_next, in_bs, nullptr, nullptr, nullptr, n, nullptr, nullptr, logp_out, workspace, B, n, coefs_host);
+  if (loss) {
+    if (loss->stats_rows && (reinterpret_cast<uintptr_t>(loss->stats_rows) % 16) != 0) return MIXGRPO_EINVAL;   // rows are float4
+    p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
+    p.loss.accumulate = loss->accumulate ? 1 : 0;
+  }
+  set_early(p, flags);
+  const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
+  const int src = MIXGRPO_SRC_GIVEN;
+  if (family == kFlow) {
+    if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
+    if (rnd) return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, true, false>(p, B, src, vec, st);
+    return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, false, false>(p, B, src, vec, st);
+  }
+  return policy_fwd_dance(p, v_dtype, B, vec, rnd, st);
+}
+
+namespace mg {
+__global__ void philox_advance_kernel(unsigned long long* state, unsigned long long inc) {
+  pdl_prologue();
+  state[1] += inc;
+}
+}  // namespace mg
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_philox_advance(uint64_t* device_state, uint64_t increment, void* stream) {
+  if (!device_state || (reinterpret_cast<uintptr_t>(device_state) % 8) != 0) return MIXGRPO_EINVAL;
+  launch_pdl(philox_advance_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<unsigned long long*>(device_state),
+             (unsigned long long)increment);
+  return (int)cudaGetLastError();
+}

@@ -16,6 +16,7 @@
 // log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> CTA -> ONE packed fixed-point atomicAdd per
 // CTA (count + sum in a 64-bit word): order-independent, hence bitwise reproducible; the last arriver
 // writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below.
+#pragma once
 #include "step_math.cuh"
 
 namespace mg {
@@ -36,8 +37,33 @@ struct StepParams {
   int B, tiles;
   mixgrpo_step_coefs k;
   unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
+  const unsigned long long* philox_state;          // SRC_PHILOX, graph-safe: device {seed, base offset} (or nullptr)
   LossParams loss;          // fused policy path (SRC_GIVEN only): old log-probs / advantages / stats rows, or nullptrs
+  int early;                // programmatic dependent launch: 0 = wait before any load, 1 = v / noise first, 2 = every input first
+  // optional second output: x_next (or x0) unpacked to (B,C,H,W) and de-normalised for the VAE (TR:102-115, TR:286-287)
+  float* decode_out;
+  int dC, dH, dW, d_from_x0, d_recip;
+  float d_div, d_shift;
 };
+
+// (B, S, 4C) packed scalars [i, i+8) of sample b -> (B, C, H, W): two channels x (2 x 2) patch = four 8-byte stores; a warp's
+// 32 threads cover 4 tokens x 64 channels, i.e. for each (channel, row) one fully written 32-byte sector.
+__device__ __forceinline__ void store_decoded(const StepParams& p, int b, long long i, const float (&r)[kVec]) {
+  const int c4 = 4 * p.dC, Wp = p.dW >> 1;
+  const long long tok = i / c4;
+  const int c0 = (int)(i - tok * c4) >> 2;
+  const int hp = (int)(tok / Wp), wp = (int)(tok - (long long)hp * Wp);
+  const float inv = __fdiv_rn(1.f, p.d_div);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {                    // q = cc*2 + dh
+    float a0 = r[2 * q], a1 = r[2 * q + 1];
+    if (p.d_recip) { a0 = __fmul_rn(a0, inv); a1 = __fmul_rn(a1, inv); }       // torch's CUDA div-by-scalar: a * (1/b)
+    else { a0 = __fdiv_rn(a0, p.d_div); a1 = __fdiv_rn(a1, p.d_div); }          // true division (torch CPU)
+    a0 = __fadd_rn(a0, p.d_shift); a1 = __fadd_rn(a1, p.d_shift);
+    float* dst = p.decode_out + (((long long)b * p.dC + c0 + (q >> 1)) * p.dH + 2 * hp + (q & 1)) * (long long)p.dW + 2 * wp;
+    *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+  }
+}
 
 // ------------------------------------------------------------------ the streaming kernel
 // Grid (ctas_per_sample, B); CTA = 256 threads; a CTA-tile is 2048 consecutive scalars of one sample and
@@ -54,8 +80,9 @@ struct StepParams {
 //   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in; the CTA
 //   whose returned count is the last one owns the complete sum in (old + mine), writes
 //   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
-//   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2); a contribution that is not finite
-//   or would overflow the field (mean squared normalised residual > 510) poisons the sample -> NaN.
+//   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2).  A share too large for the field (> 255/ctas)
+//   goes into the record's 64-bit side accumulator instead (packed_share / packed_total in step_math.cuh), so the
+//   log-prob stays finite like the reference's up to |d|/s ~ 16000; only a non-finite share gives NaN.
 
 template <class T, bool VECTOR>
 __device__ __forceinline__ void load_tile(const T* base, long long off, long long n, float (&r)[kVec]) {
@@ -86,10 +113,15 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
 }
 
 // OUT (compile time): 0 = neither x0 nor mean is stored (the rollout driver's steps: x0 is dead code), 1 = x0, 2 = x0 + mean
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT>
-__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE)) ? 4 : (SRC == MIXGRPO_SRC_PHILOX ? 5 : 6))
+// DEC (compile time): also emit the decode-ready tensor (mixgrpo_step_ext) — its own instantiations, so the 24 steps of a
+// rollout that do not need it keep their register budget
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, bool DEC>
+__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE) || DEC || SRC == MIXGRPO_SRC_PHILOX) ? 4 : 6)
 step_kernel(const __grid_constant__ StepParams p) {
-  pdl_prologue();
+  // Programmatic dependent launch: inputs the immediately preceding launch cannot have written are requested BEFORE
+  // griddepcontrol.wait, so their DRAM latency overlaps that launch's drain (MIXGRPO_FLAG_PDL_EARLY_V / _EARLY_LOADS)
+  // (the host only sets p.early when every CTA owns exactly one tile, so "first iteration" is the only iteration)
+  if (p.early == 0) pdl_prologue();
   const int b = blockIdx.y;
   const long long n = p.n;
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
@@ -102,14 +134,17 @@ step_kernel(const __grid_constant__ StepParams p) {
     if (VECTOR && off + threadIdx.x * kVec >= n) continue;
     float v[kVec], x[kVec], a[kVec], m1[kVec], m2[kVec];
     load_tile<VT, VECTOR>(vp, off, n, v);
-    load_tile<float, VECTOR>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
+    if (p.early == 1) pdl_prologue();
+    load_tile<float, VECTOR>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_PHILOX) {     // draw the noise here: element e -> component e%4 of Philox(e/4)
+      unsigned long long ph_seed = p.philox_seed, ph_off = p.philox_offset;
+      if (p.philox_state) { ph_seed = __ldg(p.philox_state); ph_off += __ldg(p.philox_state + 1); }   // graph-safe state
       if constexpr (VECTOR) {
         const unsigned long long e0 = (unsigned long long)b * n + off + threadIdx.x * kVec;
         float z0[4], z1[4];
-        philox_normal4(e0 >> 2, p.philox_seed, p.philox_offset, z0);
-        philox_normal4((e0 >> 2) + 1, p.philox_seed, p.philox_offset, z1);
+        philox_normal4(e0 >> 2, ph_seed, ph_off, z0);
+        philox_normal4((e0 >> 2) + 1, ph_seed, ph_off, z1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { a[j] = z0[j]; a[4 + j] = z1[j]; }
       } else {
@@ -117,7 +152,7 @@ step_kernel(const __grid_constant__ StepParams p) {
         for (int j = 0; j < kVec; ++j) {
           const unsigned long long e = (unsigned long long)b * n + off + j * kThreads + threadIdx.x;
           float z[4];
-          philox_normal4(e >> 2, p.philox_seed, p.philox_offset, z);
+          philox_normal4(e >> 2, ph_seed, ph_off, z);
           a[j] = z[e & 3];
         }
       }
@@ -126,6 +161,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR>(p.x_in + (long long)b * p.in_bs, off, n, a);
     if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
     if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
+    if (p.early == 2) pdl_prologue();
 
     float xn[kVec], x0[OUT >= 1 ? kVec : 2], mu[OUT == 2 ? kVec : 2];
 #pragma unroll
@@ -149,6 +185,10 @@ step_kernel(const __grid_constant__ StepParams p) {
     }
     if constexpr (OUT >= 1) store_tile<VECTOR>(p.x0_out + (long long)b * n, off, n, x0);
     if constexpr (OUT == 2) store_tile<VECTOR>(p.mean_out + (long long)b * n, off, n, mu);
+    if constexpr (DEC) {                           // the rollout's last step: the VAE's input leaves from the same registers
+      if constexpr (OUT >= 1) { if (p.d_from_x0) store_decoded(p, b, off + threadIdx.x * kVec, x0); else store_decoded(p, b, off + threadIdx.x * kVec, xn); }
+      else store_decoded(p, b, off + threadIdx.x * kVec, xn);
+    }
   }
   if (p.logp_out == nullptr) return;
 
@@ -162,19 +202,12 @@ step_kernel(const __grid_constant__ StepParams p) {
   t = warp_sum(t);
   if (lane == 0) {
     const int ctas = gridDim.x;
-    float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
-    const float cap = 255.0f / (float)ctas;
-    unsigned long long add = 1ull;
-    if (!(r >= 0.f && r <= cap)) {                 // NaN, inf, negative (two_var < 0) or would overflow
-      add += 1ull << kCountBits;
-      r = 0.f;
-    }
-    add += __float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits);
-    const unsigned long long old = atomicAdd(&p.acc[kWsStride * b], add);
+    const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
+    unsigned long long* rec = p.acc + kWsStride * b;
+    const unsigned long long add = packed_share(r, ctas, rec);
+    const unsigned long long old = atomicAdd(rec, add);
     if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
-      const unsigned long long tot = old + add;
-      float q = (float)((double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0));
-      if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) q = __int_as_float(0x7fc00000);
+      const float q = packed_total(old + add, rec);
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
       p.logp_out[b] = lp;
@@ -197,24 +230,28 @@ step_kernel(const __grid_constant__ StepParams p) {
 }
 
 // ------------------------------------------------------------------ host-side dispatch
-static int g_max_ctas_per_sample = kMaxCtasPerSample;   // bench knob (mixgrpo_set_tuning key 0)
-int g_use_pdl = 1;                                      // bench knob (key 1): programmatic dependent launch on/off
+extern int g_max_ctas_per_sample;                       // bench knob (mixgrpo_set_tuning key 0), defined in step_flow.cu
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT>
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, bool DEC>
 static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
+  if (ctas != p.tiles || !VECTOR) p.early = 0;           // early loads assume one tile per CTA (no loop-carried state in the kernel)
   dim3 grid((unsigned)ctas, (unsigned)p.B);
-  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT>, grid, kThreads, 0, st, p);
+  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT, DEC>, grid, kThreads, 0, st, p);
   return (int)cudaGetLastError();
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, int OUT>
 static int pick_vec(StepParams& p, bool vec_ok, cudaStream_t st) {
-  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, OUT>(p, st);
-  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT>(p, st);
+  if (p.decode_out) {                                      // set_ext() admitted it: vector path, a computed x_next (or x0)
+    if constexpr (SRC != MIXGRPO_SRC_GIVEN && OUT <= 1) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, true>(p, st);
+    else return MIXGRPO_EUNSUPPORTED;                      // not together with the mean output
+  }
+  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, OUT, false>(p, st);
+  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, false>(p, st);
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE>
@@ -244,7 +281,7 @@ static int pick_src(StepParams& p, int64_t B, int src, bool vec_ok, cudaStream_t
   return MIXGRPO_EINVAL;
 }
 
-static bool check_common(const void* v, const float* x, int64_t B, int64_t n, int v_dtype, void* ws, int64_t ws_bytes,
+static inline bool check_common(const void* v, const float* x, int64_t B, int64_t n, int v_dtype, void* ws, int64_t ws_bytes,
                          float* logp, int* err) {
   // grid.y carries the sample index; tile indices are 32-bit inside the kernel
   if (!v || !x || B <= 0 || B > 65535 || n <= 0 || (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) ||
@@ -259,7 +296,7 @@ static bool check_common(const void* v, const float* x, int64_t B, int64_t n, in
   return true;
 }
 
-static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, const void* noise, const float* x_in,
+static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, const void* noise, const float* x_in,
                  int64_t in_bs, const float* m1, const float* m2, float* x_out, int64_t out_bs, float* x0_out,
                  float* mean_out, float* logp_out, void* ws, int64_t B, int64_t n, const mixgrpo_step_coefs* k) {
   p.v = v; p.x = x; p.noise = noise; p.x_in = x_in; p.m1 = m1; p.m2 = m2;
@@ -268,11 +305,37 @@ static void fill(StepParams& p, const void* v, const float* x, int64_t x_bs, con
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
   p.B = (int)B; p.tiles = 0; p.k = *k;
   p.philox_seed = p.philox_offset = 0ull;
+  p.philox_state = nullptr;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
+  p.early = 0;
+  p.decode_out = nullptr; p.dC = p.dH = p.dW = p.d_from_x0 = p.d_recip = 0; p.d_div = 1.f; p.d_shift = 0.f;
+}
+
+static inline void set_philox(StepParams& p, const void* noise_host) {
+  const mixgrpo_philox_args* ph = static_cast<const mixgrpo_philox_args*>(noise_host);
+  p.philox_seed = ph->seed; p.philox_offset = ph->offset;
+  p.philox_state = reinterpret_cast<const unsigned long long*>(ph->device_state);
+}
+
+static inline void set_early(StepParams& p, unsigned flags) {
+  p.early = (flags & MIXGRPO_FLAG_PDL_EARLY_LOADS) ? 2 : ((flags & MIXGRPO_FLAG_PDL_EARLY_V) ? 1 : 0);
+}
+
+// validates and installs the optional decode output; returns 0 or a MIXGRPO_E* code
+static inline int set_ext(StepParams& p, const mixgrpo_step_ext* ext, int64_t n, bool vec, int src) {
+  if (!ext || !ext->decode_out) return 0;
+  if (ext->C <= 0 || ext->H <= 0 || ext->W <= 0 || (ext->C % 2) || (ext->H % 2) || (ext->W % 2) || (int64_t)ext->C * ext->H * ext->W != n ||
+      !(ext->divisor != 0.f)) return MIXGRPO_EINVAL;
+  if (ext->from_x0 ? !p.x0_out : (src == MIXGRPO_SRC_GIVEN)) return MIXGRPO_EINVAL;   // the decoded tensor must be one this launch computes
+  if (!vec || !aligned(ext->decode_out, 8)) return MIXGRPO_EUNSUPPORTED;
+  p.decode_out = ext->decode_out; p.dC = ext->C; p.dH = ext->H; p.dW = ext->W;
+  p.d_from_x0 = ext->from_x0 ? 1 : 0; p.d_div = ext->divisor; p.d_shift = ext->shift;
+  p.d_recip = ext->reciprocal ? 1 : 0;
+  return 0;
 }
 
 // 256-bit path needs 32-B aligned fp32 streams, 16-B aligned bf16 streams and n, strides % 8 == 0.
-static bool vector_ok(const StepParams& p, int v_dtype, int noise_dtype, int64_t n) {
+static inline bool vector_ok(const StepParams& p, int v_dtype, int noise_dtype, int64_t n) {
   bool ok = (n % kVec == 0) && (p.x_bs % kVec == 0) && (p.in_bs % kVec == 0) && (p.out_bs % kVec == 0);
   ok = ok && aligned(p.v, v_dtype == MIXGRPO_BF16 ? 16 : 32) && aligned(p.x, 32);
   ok = ok && aligned(p.noise, noise_dtype == MIXGRPO_BF16 ? 16 : 32) && aligned(p.x_in, 32);
@@ -281,132 +344,3 @@ static bool vector_ok(const StepParams& p, int v_dtype, int noise_dtype, int64_t
 }
 
 }  // namespace mg
-
-using namespace mg;
-
-extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n) {
-  if (B <= 0 || n <= 0) return 0;
-  // one 16-byte record per sample: { packed 64-bit accumulator | 32-bit epoch | 32-bit status (record 0) } — the layout
-  // does not depend on B, so calls with different batch sizes can share one zero-initialised allocation
-  return ((B * (int64_t)(kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
-}
-
-extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
-  if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
-  if (key >= 3 && key <= 5) return mixgrpo_policy_set_tuning(key, value);
-  if (key == 1) {
-    if (value != 0 && value != 1) return MIXGRPO_EINVAL;
-    const int old = g_use_pdl;
-    g_use_pdl = value;
-    return old;
-  }
-  if (key != 0 || value < 1 || value > kMaxCtasPerSample) return MIXGRPO_EINVAL;
-  const int old = g_max_ctas_per_sample;
-  g_max_ctas_per_sample = value;
-  return old;
-}
-
-extern "C" __attribute__((visibility("default"))) int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs, const void* noise,
-                                 const float* x_next_in, int64_t in_bs, float* x_next_out, int64_t out_bs,
-                                 float* x0_out, float* mean_out, float* logp_out, void* workspace,
-                                 int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                                 int src, unsigned flags, void* stream) {
-  int err = 0;
-  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
-  if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
-  StepParams p;
-  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
-  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = static_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
-  const bool vec = vector_ok(p, v_dtype, v_dtype, n);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
-  if (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, true, false>(p, B, src, vec, st);
-  return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, false, false>(p, B, src, vec, st);
-}
-
-extern "C" __attribute__((visibility("default"))) int mixgrpo_dance_step(const void* v, int v_dtype, const float* x, int64_t x_bs, const float* noise,
-                                  const float* x_next_in, int64_t in_bs, float* x_next_out, int64_t out_bs,
-                                  float* x0_out, float* mean_out, float* logp_out, void* workspace,
-                                  int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                                  int src, int sde_solver, unsigned flags, void* stream) {
-  int err = 0;
-  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
-  if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
-  StepParams p;
-  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
-  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = reinterpret_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
-  const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
-  if (v_dtype == MIXGRPO_F32) {
-    return sde_solver ? pick_src<kDance, float, float, 1, false, true>(p, B, src, vec, st)
-                      : pick_src<kDance, float, float, 1, false, false>(p, B, src, vec, st);
-  }
-  if (rnd) {
-    return sde_solver ? pick_src<kDance, __nv_bfloat16, float, 1, true, true>(p, B, src, vec, st)
-                      : pick_src<kDance, __nv_bfloat16, float, 1, true, false>(p, B, src, vec, st);
-  }
-  return sde_solver ? pick_src<kDance, __nv_bfloat16, float, 1, false, true>(p, B, src, vec, st)
-                    : pick_src<kDance, __nv_bfloat16, float, 1, false, false>(p, B, src, vec, st);
-}
-
-template <int ORDER>
-static int dpm_dispatch(StepParams& p, int v_dtype, int64_t B, int src, bool vec, bool rnd, cudaStream_t st) {
-  if (v_dtype == MIXGRPO_F32) return pick_src<kDpm, float, float, ORDER, false, false>(p, B, src, vec, st);
-  if (rnd) return pick_src<kDpm, __nv_bfloat16, float, ORDER, true, false>(p, B, src, vec, st);
-  return pick_src<kDpm, __nv_bfloat16, float, ORDER, false, false>(p, B, src, vec, st);
-}
-
-extern "C" __attribute__((visibility("default"))) int mixgrpo_dpm_step(const void* v, int v_dtype, const float* x, int64_t x_bs, const float* noise,
-                                const float* m1, const float* m2, int order, float* x_next_out, int64_t out_bs,
-                                float* x0_out, float* mean_out, float* logp_out, void* workspace,
-                                int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
-                                int src, unsigned flags, void* stream) {
-  int err = 0;
-  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
-  if (order < 1 || order > 3 || (order >= 2 && !m1) || (order == 3 && !m2)) return MIXGRPO_EINVAL;
-  if ((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) return MIXGRPO_EINVAL;
-  StepParams p;
-  fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, nullptr, n, m1, m2, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
-  if (src == MIXGRPO_SRC_PHILOX) { const mixgrpo_philox_args* ph = reinterpret_cast<const mixgrpo_philox_args*>(noise); p.philox_seed = ph->seed; p.philox_offset = ph->offset; }
-  const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
-  switch (order) {
-    case 1: return dpm_dispatch<1>(p, v_dtype, B, src, vec, rnd, st);
-    case 2: return dpm_dispatch<2>(p, v_dtype, B, src, vec, rnd, st);
-    default: return dpm_dispatch<3>(p, v_dtype, B, src, vec, rnd, st);
-  }
-}
-
-// Fused policy-update forward: log p(x_next | x, v) for the stored transition (TR:149-168 via grpo_one_step) AND the
-// per-sample clipped-ratio loss terms (TR:560-583) accumulated into stats_rows — one launch, nothing else.
-extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int family, const void* v, int v_dtype, const float* x, int64_t x_bs,
-                                  const float* x_next, int64_t in_bs, float* logp_out, void* workspace, int64_t workspace_bytes,
-                                  int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host, const mixgrpo_loss_args* loss,
-                                  unsigned flags, void* stream) {
-  int err = 0;
-  if (!coefs_host || !logp_out || !x_next || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err))
-    return err ? err : MIXGRPO_EINVAL;
-  if (family != kFlow && family != kDance) return MIXGRPO_EINVAL;
-  if (loss && (!loss->old_logp || !loss->advantages)) return MIXGRPO_EINVAL;
-  StepParams p;
-  fill(p, v, x, x_bs, nullptr, x_next, in_bs, nullptr, nullptr, nullptr, n, nullptr, nullptr, logp_out, workspace, B, n, coefs_host);
-  if (loss) {
-    if (loss->stats_rows && (reinterpret_cast<uintptr_t>(loss->stats_rows) % 16) != 0) return MIXGRPO_EINVAL;   // rows are float4
-    p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
-    p.loss.accumulate = loss->accumulate ? 1 : 0;
-  }
-  const bool vec = vector_ok(p, v_dtype, MIXGRPO_F32, n);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
-  const int src = MIXGRPO_SRC_GIVEN;
-  if (family == kFlow) {
-    if (v_dtype == MIXGRPO_F32) return pick_src<kFlow, float, float, 1, false, false>(p, B, src, vec, st);
-    if (rnd) return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, true, false>(p, B, src, vec, st);
-    return pick_src<kFlow, __nv_bfloat16, __nv_bfloat16, 1, false, false>(p, B, src, vec, st);
-  }
-  if (v_dtype == MIXGRPO_F32) return pick_src<kDance, float, float, 1, false, true>(p, B, src, vec, st);
-  if (rnd) return pick_src<kDance, __nv_bfloat16, float, 1, true, true>(p, B, src, vec, st);
-  return pick_src<kDance, __nv_bfloat16, float, 1, false, true>(p, B, src, vec, st);
-}

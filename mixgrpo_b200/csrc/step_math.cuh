@@ -10,12 +10,47 @@ namespace mg {
 
 enum Family { kFlow = 0, kDance = 1, kDpm = 2 };
 
-// packed log-prob accumulator (one 64-bit word per sample): [ sum Q8.32 : 40 | poison : 12 | arrivals : 12 ]
+// packed log-prob accumulator (one 64-bit word per sample): [ sum Q8.32 : 40 | wide-share count : 12 | arrivals : 12 ]
 constexpr int kTile = kThreads * kVec;          // scalars per CTA-tile
 constexpr int kCountBits = 12, kPoisonBits = 12;
 constexpr int kMaxCtasPerSample = (1 << kCountBits) - 1;
-// workspace record per sample (in 64-bit words): { accumulator, { epoch : 32 | status : 32 } } — see mixgrpo_step_workspace_bytes
-constexpr int kWsStride = 2;
+// workspace record per sample (in 64-bit words): { accumulator, { epoch : 32 | status : 32 }, wide side accumulator, pad }
+// — see mixgrpo_step_workspace_bytes
+constexpr int kWsStride = 4;
+constexpr int kWsWide = 2;                      // word index of the side accumulator inside a record
+constexpr float kWideCap = 134217728.f;         // 2^27: largest per-CTA share the side accumulator takes (4095 CTAs x 2^27 x 2^24 < 2^63)
+
+// The packed word holds shares of mean(d^2 / 2 s^2) up to 255/ctas each — ample for any transition a sane policy
+// produces (the value is ~0.5 on the rollout's own samples).  The reference, though, returns a FINITE log-prob however far
+// x_next is from the mean (SU:201-208), so a share that does not fit is not dropped: it goes, as Q39.24 fixed point, into
+// the record's 64-bit side accumulator (integer adds: still order-independent, still bitwise reproducible) and the CTA
+// only flags the fact in the packed word's 12-bit "wide" count.  The finalizer — the CTA that sees the last arrival —
+// folds the side word in and re-zeroes it.  Only a non-finite / negative share, or one above 2^27 (|d|/s > 16000),
+// yields NaN.  The common path is unchanged: one atomicAdd per CTA, no fence.
+__device__ __forceinline__ unsigned long long packed_share(float r, int ctas, unsigned long long* rec) {
+  const float cap = 255.0f / (float)ctas;
+  unsigned long long add = 1ull;
+  if (!(r >= 0.f && r <= cap)) {
+    if (r > cap && r <= kWideCap) atomicAdd(rec + kWsWide, __float2ull_rn(r * 16777216.0f));
+    else atomicOr(rec + kWsWide, 1ull << 63);
+    __threadfence();                             // the side word is visible before this CTA's arrival is counted
+    add += 1ull << kCountBits;
+    r = 0.f;
+  }
+  return add + (__float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits));
+}
+
+// tot = the packed word after the LAST arrival; returns mean(d^2 / 2 s^2) of the sample
+__device__ __forceinline__ float packed_total(unsigned long long tot, unsigned long long* rec) {
+  double q = (double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0);
+  if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) {
+    __threadfence();
+    const unsigned long long wide = atomicExch(rec + kWsWide, 0ull);      // read and leave zeroed for the next launch
+    if (wide >> 63) return __int_as_float(0x7fc00000);
+    q += (double)wide * (1.0 / 16777216.0);
+  }
+  return (float)q;
+}
 
 // ------------------------------------------------------------------ per-tile arithmetic
 // FAM/SRC/ORDER/RND/SDE are compile-time so each instantiation is straight-line code.

@@ -12,8 +12,8 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_ROUND_LIKE_TORCH, SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX,
-                    LossArgs, PhiloxArgs, StepCoefs)
+from ._cabi import (BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_PDL_EARLY_V, FLAG_ROUND_LIKE_TORCH, POLICY_MAX_ITEMS, SRC_DETERMINISTIC,
+                    SRC_GIVEN, SRC_NOISE, SRC_PHILOX, LossArgs, PhiloxArgs, PolicyItem, StepCoefs, StepExt)
 
 FLOW, DANCE, DPM = 0, 1, 2
 
@@ -90,10 +90,48 @@ def _workspace(device: torch.device, B: int, n: int, stream: Optional[int] = Non
     return ws
 
 
+class PhiloxState:
+    """CUDA-graph-safe state for in-kernel noise: a device vector ``{seed, base offset}`` the step kernels read at RUN time
+    (``mixgrpo_philox_args.device_state``).  A launch captured into a graph keeps only its position relative to the base
+    (``take``), and ``advance`` — one tiny launch, captured with the rollout — moves the base, so every replay draws fresh
+    noise.  Eagerly it behaves like a private generator.  (Host-read seeds/offsets, ``philox_from_generator``, would be
+    frozen into the graph: every replay would repeat the same exploration noise.)"""
+
+    def __init__(self, device, seed: int = 0, offset: int = 0):
+        self.device = torch.device(device)
+        vals = [int(seed) & 0x7FFFFFFFFFFFFFFF, int(offset) & 0x7FFFFFFFFFFFFFFF]
+        self.state = torch.tensor(vals, dtype=torch.int64).to(self.device)
+        self._pending = 0                       # numbers handed out since the last advance (host-known, constant per graph)
+
+    def take(self, numel: int) -> Tuple["PhiloxState", int]:
+        """Reserve ``numel`` normals: returns ``(self, relative offset)`` for ``fused_step(philox=...)``."""
+        rel = self._pending
+        self._pending += 4 * ((int(numel) + 3) // 4)
+        return self, rel
+
+    def advance(self) -> None:
+        """``base += everything taken since the last advance`` on the device (stream-ordered, capturable)."""
+        global launch_count
+        if self._pending == 0:
+            return
+        with _on_device(self.device):
+            rc = _cabi.lib().mixgrpo_philox_advance(self.state.data_ptr(), self._pending, _stream_ptr(self.device))
+        _cabi.check(rc, "philox_advance")
+        launch_count += 1
+        self._pending = 0
+
+
 def philox_from_generator(device: torch.device, numel: int, generator: Optional[torch.Generator] = None) -> Tuple[int, int]:
     """(seed, offset) for MIXGRPO_SRC_PHILOX taken from a torch CUDA generator (the device default when None), whose
     Philox offset is advanced past the ``numel`` normals consumed — later torch.randn calls draw fresh numbers, and
-    ``torch.manual_seed`` / ``generator.manual_seed`` reproduce the in-kernel noise too."""
+    ``torch.manual_seed`` / ``generator.manual_seed`` reproduce the in-kernel noise too.
+
+    Not capturable: the values are read on the host and would be frozen into a CUDA graph (identical noise on every
+    replay) — raises under stream capture; use a :class:`PhiloxState` there."""
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("mixgrpo_b200: in-kernel noise seeded from a torch generator cannot be captured into a CUDA graph "
+                           "(seed/offset are host values: every replay would draw the same noise); pass a "
+                           "mixgrpo_b200.ops.PhiloxState (rollout(..., philox_state=...))")
     if generator is None or generator.device.type != "cuda":
         idx = device.index if device.index is not None else torch.cuda.current_device()
         seed_src = generator
@@ -110,10 +148,16 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                m1: Optional[torch.Tensor] = None, m2: Optional[torch.Tensor] = None, order: int = 1,
                sde_solver: bool = True, out_x_next: Optional[torch.Tensor] = None, want_x0: bool = True,
                want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
-               out_logp: Optional[torch.Tensor] = None, philox: Optional[Tuple[int, int]] = None,
-               out_x0: Optional[torch.Tensor] = None):
+               out_logp: Optional[torch.Tensor] = None, philox=None,
+               out_x0: Optional[torch.Tensor] = None, early: int = 0, decode: Optional[dict] = None):
     """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
-    requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in."""
+    requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in.
+
+    ``philox``: ``(seed, offset)`` host values or ``(PhiloxState, relative offset)`` (graph-safe).
+    ``early``: 1 = model output / noise were not written by the immediately preceding launch on this stream
+    (MIXGRPO_FLAG_PDL_EARLY_V), 2 = no streamed input was (MIXGRPO_FLAG_PDL_EARLY_LOADS).
+    ``decode``: ``{"out": fp32 (B,C,H,W), "divisor": 0.3611, "shift": 0.1159, "from_x0": False, "reciprocal": False}`` —
+    the VAE's input (unpack + de-normalise, TR:102-115, TR:286-287) written by this launch as a second output."""
     global launch_count
     lib = _cabi.lib()
     _require_cuda(v, "model_output")
@@ -151,7 +195,10 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     elif src == SRC_PHILOX:
         if philox is None:
             raise ValueError("mixgrpo_b200: in-kernel noise needs philox=(seed, offset)")
-        pa = PhiloxArgs(int(philox[0]) & 0xFFFFFFFFFFFFFFFF, int(philox[1]) & 0xFFFFFFFFFFFFFFFF)
+        if isinstance(philox[0], PhiloxState):
+            pa = PhiloxArgs(0, int(philox[1]) & 0xFFFFFFFFFFFFFFFF, philox[0].state.data_ptr())
+        else:
+            pa = PhiloxArgs(int(philox[0]) & 0xFFFFFFFFFFFFFFFF, int(philox[1]) & 0xFFFFFFFFFFFFFFFF, None)
         keep.append(pa)
         noise_p = C.cast(C.pointer(pa), C.c_void_p)          # HOST pointer, read during the call
     elif src == SRC_GIVEN:
@@ -202,18 +249,28 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
             logp = torch.empty((B,), dtype=torch.float32, device=dev)
     st = _stream_ptr(dev)
     ws = _workspace(dev, B, n, st) if want_logp else None
-    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early == 2 else (FLAG_PDL_EARLY_V if early == 1 else 0))
+    ext = None
+    if decode is not None:
+        d_out = decode["out"]
+        _require_cuda(d_out, "decode['out']")
+        if d_out.dtype != torch.float32 or d_out.dim() != 4 or d_out.shape[0] != B or d_out[0].numel() != n or not d_out.is_contiguous():
+            raise ValueError("mixgrpo_b200: decode['out'] must be a contiguous fp32 (B, C, H, W) tensor with C*H*W == elements per sample")
+        xe = StepExt(d_out.data_ptr(), d_out.shape[1], d_out.shape[2], d_out.shape[3], float(decode.get("divisor", 1.0)),
+                     float(decode.get("shift", 0.0)), 1 if decode.get("from_x0", False) else 0, 1 if decode.get("reciprocal", False) else 0)
+        keep.append(xe)
+        ext = C.byref(xe)
     common_out = (out_p, out_bs, x0.data_ptr() if want_x0 else None, mean.data_ptr() if want_mean else None,
                   logp.data_ptr() if want_logp else None, ws.data_ptr() if want_logp else None,
                   ws.numel() if want_logp else 0, B, n, C.byref(coefs))
     with _on_device(dev):
         if family == FLOW:
-            rc = lib.mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src, flags, st)
+            rc = lib.mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src, flags, st, ext)
         elif family == DANCE:
             rc = lib.mixgrpo_dance_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src,
-                                        1 if sde_solver else 0, flags, st)
+                                        1 if sde_solver else 0, flags, st, ext)
         elif family == DPM:
-            rc = lib.mixgrpo_dpm_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, m1_p, m2_p, order, *common_out, src, flags, st)
+            rc = lib.mixgrpo_dpm_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, m1_p, m2_p, order, *common_out, src, flags, st, ext)
         else:
             raise ValueError(family)
     _cabi.check(rc, ("flow_step", "dance_step", "dpm_step")[family])
@@ -275,8 +332,9 @@ def _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_co
 def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, coefs: StepCoefs, old_logp: torch.Tensor,
                    advantages: torch.Tensor, clip_range: float, adv_clip_max: float, kl_coeff: float, denom: float,
                    stats_rows: Optional[torch.Tensor] = None, round_like_torch: bool = False,
-                   out_logp: Optional[torch.Tensor] = None, accumulate: bool = True) -> torch.Tensor:
-    """Fused policy-update forward (mixgrpo_policy_fwd): new log-probs [B]; per-sample loss terms += stats_rows."""
+                   out_logp: Optional[torch.Tensor] = None, accumulate: bool = True, early_loads: bool = False) -> torch.Tensor:
+    """Fused policy-update forward (mixgrpo_policy_fwd): new log-probs [B]; per-sample loss terms += stats_rows.
+    ``early_loads``: no input tensor was written by the launch immediately before this one on the stream."""
     global launch_count
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample")):
@@ -291,7 +349,7 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
     la, keep = _loss_args(old_logp, advantages, stats_rows, clip_range, adv_clip_max, kl_coeff, denom, B, dev, accumulate)
     logp = out_logp if out_logp is not None else torch.empty((B,), dtype=torch.float32, device=dev)
     ws = _workspace(dev, B, n)
-    flags = FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0
+    flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early_loads else 0)
     with _on_device(dev):
         rc = lib.mixgrpo_policy_fwd(family, v.data_ptr(), vd, x.data_ptr(), x_bs, x_next.data_ptr(), in_bs, logp.data_ptr(), ws.data_ptr(),
                                     ws.numel(), B, n, C.byref(coefs), C.byref(la), flags, _stream_ptr(dev))
@@ -329,6 +387,104 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     launch_count += 1
     del keep
     return grad_v
+
+
+def _policy_items(family, vs, xs, x_nexts, coefs_list, old_logps, logps, stats_rows, grads, B, n, dev):
+    if not (0 < len(vs) <= POLICY_MAX_ITEMS):
+        raise ValueError(f"mixgrpo_b200: 1..{POLICY_MAX_ITEMS} items per batched policy launch, got {len(vs)}")
+    items = (PolicyItem * len(vs))()
+    keep = []
+    for j in range(len(vs)):
+        v = vs[j]
+        for t, nm in ((v, "model_output"), (xs[j], "latents"), (x_nexts[j], "prev_sample")):
+            _require_cuda(t, nm)
+        if v.dtype != vs[0].dtype or v.shape != vs[0].shape:
+            raise ValueError("mixgrpo_b200: every item of a batched policy launch must have the same shape and dtype")
+        v = v if v.is_contiguous() else v.contiguous()
+        x, x_bs = _rows(xs[j].to(torch.float32), "latents")
+        xn, in_bs = _rows(x_nexts[j].to(torch.float32), "prev_sample")
+        ol = old_logps[j].detach().to(torch.float32).contiguous().view(-1)
+        if ol.numel() != B or logps[j].numel() != B or logps[j].dtype != torch.float32 or not logps[j].is_contiguous():
+            raise ValueError("mixgrpo_b200: log-prob vectors must be contiguous fp32 [B]")
+        it = items[j]
+        it.v, it.x, it.x_next, it.x_bs, it.in_bs = v.data_ptr(), x.data_ptr(), xn.data_ptr(), x_bs, in_bs
+        it.logp, it.old_logp = logps[j].data_ptr(), ol.data_ptr()
+        it.stats_rows = None
+        if stats_rows is not None and stats_rows[j] is not None:
+            r = stats_rows[j]
+            if r.dtype != torch.float32 or tuple(r.shape) != (B, 4) or not r.is_contiguous() or r.device != dev:
+                raise ValueError("mixgrpo_b200: stats_rows must be contiguous fp32 [B, 4] tensors on the same device")
+            it.stats_rows = r.data_ptr()
+        it.grad_v = grads[j].data_ptr() if grads is not None else None
+        it.coefs = coefs_list[j]
+        keep += [v, x, xn, ol]
+    return items, keep
+
+
+def policy_forward_multi(family: int, vs, xs, x_nexts, coefs_list, old_logps, advantages: torch.Tensor, clip_range: float,
+                         adv_clip_max: float, kl_coeff: float, denom: float, stats_rows=None, round_like_torch: bool = False,
+                         out_logps: Optional[torch.Tensor] = None, accumulate: bool = True, early_loads: bool = False):
+    """The window's policy forwards as ONE launch (mixgrpo_policy_fwd_multi): item j = (vs[j], xs[j], x_nexts[j], coefs_list[j],
+    old_logps[j], stats_rows[j]).  Returns the new log-probs ``[n_items, B]``, or ``None`` — nothing launched — for ragged /
+    unaligned tensors (call ``policy_forward`` per item then).  Bit-identical to the per-item launches."""
+    global launch_count
+    lib = _cabi.lib()
+    v0 = vs[0]
+    _require_cuda(v0, "model_output")
+    vd = _dtype_code(v0, "model_output")
+    B, n, dev = v0.shape[0], v0[0].numel(), v0.device
+    J = len(vs)
+    logps = out_logps if out_logps is not None else torch.empty((J, B), dtype=torch.float32, device=dev)
+    if B == 0:
+        return logps
+    items, keep = _policy_items(family, vs, xs, x_nexts, coefs_list, old_logps, [logps[j] for j in range(J)], stats_rows, None, B, n, dev)
+    _require_cuda(advantages, "advantages")
+    adv = advantages.detach().to(torch.float32).contiguous().view(-1)
+    if adv.numel() != B:
+        raise ValueError("mixgrpo_b200: `advantages` must have one entry per sample")
+    ws = _workspace(dev, B * J, n)
+    flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early_loads else 0)
+    with _on_device(dev):
+        rc = lib.mixgrpo_policy_fwd_multi(family, vd, items, J, adv.data_ptr(), float(clip_range), float(adv_clip_max), float(kl_coeff),
+                                          float(denom), 1 if accumulate else 0, ws.data_ptr(), ws.numel(), B, n, flags, _stream_ptr(dev))
+    del keep
+    if rc == _cabi.EUNSUPPORTED:
+        return None
+    _cabi.check(rc, "policy_fwd_multi")
+    launch_count += 1
+    return logps
+
+
+def policy_backward_multi(family: int, vs, xs, x_nexts, new_logps: torch.Tensor, coefs_list, old_logps, advantages: torch.Tensor,
+                          clip_range: float, adv_clip_max: float, kl_coeff: float, denom: float, round_like_torch: bool = False,
+                          early_loads: bool = False, out_grads=None):
+    """The window's policy backwards as ONE launch (mixgrpo_policy_bwd_multi): ``grads[j] = dloss/d vs[j]``; ``None`` when the
+    batched entry point does not cover the tensors."""
+    global launch_count
+    lib = _cabi.lib()
+    v0 = vs[0]
+    vd = _dtype_code(v0, "model_output")
+    B, n, dev = v0.shape[0], v0[0].numel(), v0.device
+    J = len(vs)
+    grads = out_grads if out_grads is not None else [torch.empty_like(v0, memory_format=torch.contiguous_format) for _ in range(J)]
+    if B == 0:
+        return grads
+    for g in grads:
+        if g.dtype != v0.dtype or g.shape != v0.shape or not g.is_contiguous():
+            raise ValueError("mixgrpo_b200: gradient buffers must match the model output's dtype/shape and be contiguous")
+    nl = new_logps.detach()
+    items, keep = _policy_items(family, vs, xs, x_nexts, coefs_list, old_logps, [nl[j] for j in range(J)], None, grads, B, n, dev)
+    adv = advantages.detach().to(torch.float32).contiguous().view(-1)
+    flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early_loads else 0)
+    with _on_device(dev):
+        rc = lib.mixgrpo_policy_bwd_multi(family, vd, items, J, adv.data_ptr(), float(clip_range), float(adv_clip_max), float(kl_coeff),
+                                          float(denom), B, n, flags, _stream_ptr(dev))
+    del keep
+    if rc == _cabi.EUNSUPPORTED:
+        return None
+    _cabi.check(rc, "policy_bwd_multi")
+    launch_count += 1
+    return grads
 
 
 def policy_step(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, coefs: StepCoefs, old_logp: torch.Tensor,

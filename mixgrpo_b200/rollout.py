@@ -44,6 +44,10 @@ class SamplerConfig:
     drop_last_sample: bool = False
     rounding: str = "auto"
     inkernel_noise: bool = False             # draw SDE noise inside the step kernel when `noises[i]` is None (no randn launch)
+    # programmatic dependent launch: the model outputs / noise handed to a sampler step are NOT written by the launch issued
+    # immediately before it on the stream (true when `model` returns precomputed tensors or when its last kernel is not the
+    # producer of v; after a real DiT forward the attribute is inert anyway) -> v / noise loads overlap the previous step's drain
+    pdl_early_v: bool = False
 
 
 def sigma_schedule(sampling_steps: int, shift: float, device=None) -> torch.Tensor:
@@ -66,10 +70,18 @@ def window_mask(sampling_steps: int, timesteps_train: Sequence[int], training_st
 
 def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.Tensor, sigmas: torch.Tensor,
             determistic: Sequence[bool], cfg: SamplerConfig, noises: Optional[Sequence[Optional[torch.Tensor]]] = None,
-            want_x0: bool = False, generator: Optional[torch.Generator] = None):
+            want_x0: bool = False, generator: Optional[torch.Generator] = None, philox_state: Optional[_ops.PhiloxState] = None,
+            decode: Optional[dict] = None):
     """Batched equivalent of SU:61-155.  ``model(latents, sigma_float, step) -> model_output`` stands for the
     DiT forward (SU:62-82).  Returns ``(z_final, latents, all_latents (B,N+1,...), all_log_probs (B,N), sigmas)``
-    where ``sigmas`` is the schedule actually used (rebuilt in Flash "post" mode, SU:33-54)."""
+    where ``sigmas`` is the schedule actually used (rebuilt in Flash "post" mode, SU:33-54).
+
+    ``philox_state``: with ``cfg.inkernel_noise``, draw from this graph-safe device state (required under CUDA-graph
+    capture; advanced once at the end of the rollout) instead of a torch generator.
+    ``decode``: ``{"height": h, "width": w, "vae_scale_factor": 8, "divisor": 0.3611, "shift": 0.1159, "reciprocal": False}`` —
+    the LAST sampler step also writes the VAE's input ``unpack_latents(latents, h, w, 8) / divisor + shift`` (TR:286-287)
+    as a second output; it is returned in ``decode["out"]`` (fp32 (B, C, H', W')).  Saves the unpack launch and one
+    read + write of the final latent."""
     mode = _mode(cfg.rounding)
     dpm_state = None
     last_sde = None
@@ -88,8 +100,18 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
     host_sig = _coefs.host_schedule(sigmas).tolist()
     x0 = None
     need_x0_last = cfg.drop_last_sample or want_x0
+    early = 1 if cfg.pdl_early_v else 0
+    dec_last = None
+    if decode is not None:
+        vsf = int(decode.get("vae_scale_factor", 8))
+        hh, ww = 2 * (int(decode["height"]) // (vsf * 2)), 2 * (int(decode["width"]) // (vsf * 2))
+        ch = z.shape[-1] // 4
+        decode["out"] = torch.empty((B, ch, hh, ww), dtype=torch.float32, device=dev)
+        dec_last = {"out": decode["out"], "divisor": decode.get("divisor", 1.0), "shift": decode.get("shift", 0.0),
+                    "from_x0": bool(cfg.drop_last_sample), "reciprocal": bool(decode.get("reciprocal", False))}
     for i in range(n_steps):
         x, out = traj[:, i], traj[:, i + 1]
+        dec = dec_last if i == n_steps - 1 else None
         v = model(z if i == 0 else x, host_sig[i], i)
         bf16_v = v.dtype == torch.bfloat16
         rnd = bf16_v and mode != "fp32"
@@ -107,7 +129,7 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
                 nz = torch.randn(v.shape, device=dev, dtype=torch.float32)
             _, x0, _, _ = _ops.fused_step(_ops.DPM, v, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
                                           noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
-                                          out_logp=logps_t[i], want_x0=True, round_like_torch=rnd)
+                                          out_logp=logps_t[i], want_x0=True, round_like_torch=rnd, early=early, decode=dec)
             dpm_state.update(x0)
             dpm_state.update_lower_order()
         else:
@@ -117,26 +139,37 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
             if determistic[i]:
                 src, nz = SRC_DETERMINISTIC, None
             elif nz is None and cfg.inkernel_noise:
-                src, ph = SRC_PHILOX, _ops.philox_from_generator(dev, v.numel(), generator)
+                src = SRC_PHILOX
+                ph = philox_state.take(v.numel()) if philox_state is not None else _ops.philox_from_generator(dev, v.numel(), generator)
             else:
                 src = SRC_NOISE
                 if nz is None:
                     nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32, generator=generator)
             _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
-                                          out_logp=logps_t[i], want_x0=keep_x0, round_like_torch=rnd)
+                                          out_logp=logps_t[i], want_x0=keep_x0, round_like_torch=rnd, early=early, decode=dec)
             if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
                 dpm_state.update(x0)
                 dpm_state.update_lower_order()
+    if philox_state is not None:
+        philox_state.advance()                                               # the next rollout (or graph replay) draws fresh noise
     z_final = traj[:, n_steps]
     latents = x0 if cfg.drop_last_sample else z_final                        # SU:149-152
     return z_final, latents, traj, logps_t.t(), sigmas
 
 
+def timestep_values(sigmas: torch.Tensor, sampling_steps: Optional[int] = None) -> List[int]:
+    """``[int(sigma * 1000) for sigma in sigma_schedule][:sampling_steps]`` (TR:401, SU:63-65): the product is taken in
+    fp32 like the reference's 0-dim tensor op — a python-double product differs by one for many (N, shift) pairs — then
+    truncated.  One host pass over the cached schedule, no device sync per entry."""
+    host = _coefs.host_schedule(sigmas)
+    vals = (host * 1000).to(torch.int64).tolist()                            # fp32 multiply, truncation toward zero = int()
+    return vals if sampling_steps is None else vals[:sampling_steps]
+
+
 def make_samples(all_latents: torch.Tensor, all_log_probs: torch.Tensor, sigmas: torch.Tensor, sampling_steps: int) -> Dict:
     """TR:400-415: the last transition is never trained, so N-1 transitions remain (views only)."""
     B = all_latents.shape[0]
-    host = _coefs.host_schedule(sigmas).tolist()
-    tvals = [int(s * 1000) for s in host][:sampling_steps]                   # TR:401
+    tvals = timestep_values(sigmas, sampling_steps)                          # TR:401
     timesteps = torch.tensor([tvals] * B, dtype=torch.long).to(all_latents.device, non_blocking=True)
     return {
         "timesteps": timesteps[:, :-1],
@@ -189,6 +222,9 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
     residuals fit on chip (up to ~8 M latent scalars, e.g. (24, 4096, 64)): ONE launch that reads every latent byte once
     (12 instead of 22 B/elem from HBM, same bits).  It is opt-in because on B200 the pair is as fast or faster: the
     backward's re-reads hit the 126 MB L2, while the single pass pays a grid-wide dependency (profiles/r01_policy_step.md)."""
+    if "dpmsolver" in cfg.dpm_algorithm_type and cfg.dpm_apply_strategy == "all":
+        raise NotImplementedError("dpm_apply_strategy='all' trains dpm_step's own fresh-noise transition (TR:169-180), not the stored "
+                                  "one: use trainer.train_window / trainer.grpo_one_step (autograd path)")
     mode = _mode(cfg.rounding)
     bf16_v = v.dtype == torch.bfloat16
     rnd = bf16_v and mode != "fp32"
@@ -212,3 +248,52 @@ def policy_update(v: torch.Tensor, latents: torch.Tensor, next_latents: torch.Te
                                   kl_coeff, denom, round_like_torch=rnd, early_loads=True)   # launched right after the forward
     return stats_rows, new_lp, grad_v
 
+
+
+def policy_update_window(vs: Sequence[torch.Tensor], all_latents: torch.Tensor, steps: Sequence[int], old_log_probs: torch.Tensor,
+                         advantages: torch.Tensor, sigmas: torch.Tensor, cfg: SamplerConfig, *, clip_range: float, adv_clip_max: float,
+                         kl_coeff: float, gradient_accumulation_steps: int, stats_rows: Optional[torch.Tensor] = None,
+                         accumulate: bool = True, early_loads: bool = False):
+    """The whole SDE window's policy update in TWO launches (mixgrpo_policy_fwd_multi / _bwd_multi): for window step
+    ``t = steps[j]`` with model output ``vs[j]``, the stored transition ``all_latents[:, t] -> all_latents[:, t+1]`` and old
+    log-probs ``old_log_probs[:, t]`` (TR:536-585 — the reference walks the (sample, step) pairs one by one; given their model
+    outputs they are independent).  Returns ``(stats_rows [J,B,4], new_log_probs [J,B], [grad_v_j])``; hand ``grad_v_j`` to
+    ``vs[j].backward``.  Bit-identical to ``policy_update`` per step; falls back to it for ragged / unaligned tensors or
+    more than 8 steps.  ``early_loads``: no input was written by the launch immediately before this call on the stream."""
+    if "dpmsolver" in cfg.dpm_algorithm_type and cfg.dpm_apply_strategy == "all":
+        raise NotImplementedError("dpm_apply_strategy='all' trains dpm_step's own transition: use trainer.train_window")
+    J = len(steps)
+    B, dev = all_latents.shape[0], all_latents.device
+    mode = _mode(cfg.rounding)
+    bf16_v = vs[0].dtype == torch.bfloat16
+    rnd = bf16_v and mode != "fp32"
+    fam = _ops.FLOW if cfg.flow_grpo_sampling else _ops.DANCE
+    table = _coefs.flow if cfg.flow_grpo_sampling else _coefs.dance
+    ks = [table(sigmas, int(t), cfg.eta, mode, bf16_v)[0] for t in steps]
+    denom = float(gradient_accumulation_steps * J)                           # TR:576
+    if stats_rows is None:
+        stats_rows = torch.zeros((J, B, 4), dtype=torch.float32, device=dev)
+        accumulate = False
+    vd = [v.detach() for v in vs]
+    xs = [all_latents[:, int(t)] for t in steps]
+    xns = [all_latents[:, int(t) + 1] for t in steps]
+    olds = [old_log_probs[:, int(t)] for t in steps]
+    new_lp = None
+    if J <= _ops.POLICY_MAX_ITEMS:
+        new_lp = _ops.policy_forward_multi(fam, vd, xs, xns, ks, olds, advantages, clip_range, adv_clip_max, kl_coeff, denom,
+                                           stats_rows=[stats_rows[j] for j in range(J)], round_like_torch=rnd, accumulate=accumulate,
+                                           early_loads=early_loads)
+    if new_lp is not None:
+        grads = _ops.policy_backward_multi(fam, vd, xs, xns, new_lp, ks, olds, advantages, clip_range, adv_clip_max, kl_coeff, denom,
+                                           round_like_torch=rnd, early_loads=True)        # right after the forward, which wrote only [J,B] floats
+        if grads is not None:
+            return stats_rows, new_lp, grads
+    new_lp = torch.empty((J, B), dtype=torch.float32, device=dev)
+    grads = []
+    for j, t in enumerate(steps):
+        _, lp, g = policy_update(vs[j], xs[j], xns[j], olds[j], advantages, sigmas, int(t), cfg, clip_range=clip_range, adv_clip_max=adv_clip_max,
+                                 kl_coeff=kl_coeff, gradient_accumulation_steps=gradient_accumulation_steps, num_train_timesteps=J,
+                                 stats_rows=stats_rows[j], accumulate=accumulate)
+        new_lp[j].copy_(lp)
+        grads.append(g)
+    return stats_rows, new_lp, grads

@@ -76,6 +76,37 @@ def _randn(shape, generator, device, dtype):
     return torch.randn(shape, generator=generator, device=device, dtype=dtype)
 
 
+def _refuse_silent_detach(model_output: torch.Tensor, what: str) -> None:
+    """The reference's log-prob is differentiable on every branch (autograd through the mean).  Branches without a
+    backward kernel here must not hand back a graph-less log-prob to a caller that will call ``.backward()``."""
+    if torch.is_grad_enabled() and model_output.requires_grad:
+        raise NotImplementedError(
+            f"mixgrpo_b200: {what} has no backward kernel (the reference only trains the stored-transition log-prob, "
+            "TR:149-180); call it under torch.no_grad() or pass a detached model_output")
+
+
+class _DPMFirstOrderLogProb(torch.autograd.Function):
+    """dpm_step(dpm_state=None, sde_solver=True) as the dpm_apply_strategy == "all" training path calls it (TR:169-180):
+    first-order update with fresh noise; the log-prob is differentiable w.r.t. model_output through the mean only
+    (``prev_sample.detach()``, SU:376-378).  Backward = mixgrpo_logprob_bwd family 2 on the sample this forward drew."""
+
+    @staticmethod
+    def forward(ctx, v, x, noise, k, rnd):
+        xn, x0, logp, _ = _ops.fused_step(_ops.DPM, v, x, k, src=SRC_NOISE, noise=noise, order=1, round_like_torch=rnd)
+        ctx.save_for_backward(v, x, xn)
+        ctx.k, ctx.rnd = k, rnd
+        ctx.mark_non_differentiable(xn, x0)
+        return logp, xn, x0
+
+    @staticmethod
+    def backward(ctx, g_logp, _g_xn, _g_x0):
+        v, x, xn = ctx.saved_tensors
+        grad_v = None
+        if ctx.needs_input_grad[0] and g_logp is not None:
+            grad_v = _ops.logprob_backward(_ops.DPM, v, x, xn, g_logp, ctx.k, ctx.rnd)
+        return grad_v, None, None, None, None
+
+
 class _TransitionLogProb(torch.autograd.Function):
     """log p(x_next | x, v) with the closed-form gradient w.r.t. v (policy-update path, TR:149-168)."""
 
@@ -123,6 +154,8 @@ def flow_grpo_step(
             "Cannot pass both generator and prev_sample. Please make sure that either `generator` or"
             " `prev_sample` stays `None`."
         )
+    _ops._require_cuda(model_output, "model_output")                  # no CPU fallback: fail before any device query
+    _ops._require_cuda(latents, "latents")
     mode = _mode(rounding)
     bf16_v = model_output.dtype == torch.bfloat16
     k, scale = _coefs.flow(sigmas, index, eta, mode, bf16_v)
@@ -132,6 +165,7 @@ def flow_grpo_step(
     if prev_sample is None:
         # rollout: the reference draws noise even when the step is deterministic (SU:188-195); only the
         # stochastic branch needs it here
+        _refuse_silent_detach(model_output, "flow_grpo_step in rollout mode (prev_sample=None)")
         if determistic:
             xn, x0, logp, mean = _ops.fused_step(_ops.FLOW, model_output, latents, k, src=SRC_DETERMINISTIC,
                                                  want_mean=return_mean, round_like_torch=rnd)
@@ -148,6 +182,7 @@ def flow_grpo_step(
     if determistic:
         # prev_sample given AND determistic: the reference overwrites prev_sample with the Euler step
         # (SU:198-199) and scores that
+        _refuse_silent_detach(model_output, "flow_grpo_step(determistic=True)")
         xn, x0, logp, mean = _ops.fused_step(_ops.FLOW, model_output, latents, k, src=SRC_DETERMINISTIC,
                                              want_mean=return_mean, round_like_torch=rnd)
         return xn, x0, logp, mean, scale_t
@@ -175,10 +210,14 @@ def dance_grpo_step(
     """SU:212-253 (DanceGRPO ``flux_step``).  ``grpo=True`` returns ``(prev_sample, pred_original_sample,
     log_prob)``; ``grpo=False`` returns ``(prev_sample_mean, pred_original_sample)``.  The log-prob omits the
     normalisation constants exactly like the reference (SU:247 is a dangling statement)."""
+    _ops._require_cuda(model_output, "model_output")
+    _ops._require_cuda(latents, "latents")
     mode = _mode(rounding)
     bf16_v = model_output.dtype == torch.bfloat16
     k, _std = _coefs.dance(sigmas, index, eta, mode, bf16_v)
     rnd = bf16_v and mode != "fp32"
+    if prev_sample is None or not sde_solver:
+        _refuse_silent_detach(model_output, "dance_grpo_step in rollout mode or with sde_solver=False")
     if not grpo:
         mean, x0, _, _ = _ops.fused_step(_ops.DANCE, model_output, latents, k, src=SRC_DETERMINISTIC, sde_solver=sde_solver,
                                          want_mean=False, want_logp=False, round_like_torch=rnd)
@@ -260,6 +299,8 @@ def dpm_step(
 ):
     """SU:273-385: multistep DPM-Solver(++) transition in x0-prediction form + its log-prob.
     Returns ``(prev_sample, x0_pred, log_prob)``; ``dpm_state`` is updated like the reference's."""
+    _ops._require_cuda(model_output, "model_output")
+    _ops._require_cuda(sample, "sample")
     mode = _mode(rounding)
     bf16_v = model_output.dtype == torch.bfloat16
     order = _dpm_order(args, step_index, len(timesteps), dpm_state)
@@ -273,14 +314,20 @@ def dpm_step(
         assert not sde_solver, "SDE solver is not supported for DPMSolver"          # SU:630
     k, _scale = _coefs.dpm(sigmas, step_index, order, args.dpm_algorithm_type, getattr(args, "dpm_solver_type", "midpoint"),
                            mode, bf16_v)
+    rnd = bf16_v and mode != "fp32"
     if sde_solver:
         if variance_noise is None:                                    # SU:318-321
             variance_noise = _randn(model_output.shape, generator, model_output.device, torch.float32)
         src, nz = SRC_NOISE, variance_noise
     else:
         src, nz = SRC_DETERMINISTIC, None
-    xn, x0, logp, _ = _ops.fused_step(_ops.DPM, model_output, sample, k, src=src, noise=nz, m1=m1, m2=m2, order=order,
-                                      round_like_torch=bf16_v and mode != "fp32")
+    if torch.is_grad_enabled() and model_output.requires_grad:
+        if not (sde_solver and order == 1):
+            _refuse_silent_detach(model_output, f"dpm_step(order={order}, sde_solver={sde_solver})")
+        logp, xn, x0 = _DPMFirstOrderLogProb.apply(model_output, sample, nz, k, rnd)      # TR:169-180
+    else:
+        xn, x0, logp, _ = _ops.fused_step(_ops.DPM, model_output, sample, k, src=src, noise=nz, m1=m1, m2=m2, order=order,
+                                          round_like_torch=rnd)
     if dpm_state is not None:
         dpm_state.update(x0)                                          # SU:313-314
         dpm_state.update_lower_order()                                # SU:369-370

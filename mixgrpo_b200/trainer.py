@@ -131,6 +131,10 @@ def train_window(args, transformer, samples: Dict, advantages: torch.Tensor, sig
         raise ValueError("per-sample step permutations (training_strategy 'all') need micro_batch == 1")
     order = list(range(B)) if order is None else [int(i) for i in order]
     contiguous = order == list(range(B))
+    # dpm_apply_strategy == "all" trains a DIFFERENT objective (TR:169-180): dpm_step draws fresh noise and scores its own
+    # sample, ignoring the stored next latent — so it cannot use the fused stored-transition kernels.  It goes through
+    # grpo_one_step (differentiable first-order DPM log-prob) + grpo_loss + autograd, one launch each.
+    dpm_all = "dpmsolver" in getattr(args, "dpm_algorithm_type", "null") and getattr(args, "dpm_apply_strategy", "post") == "all"
     for lo in range(0, len(order), micro_batch):
         ids = order[lo:lo + micro_batch]
         # a run of consecutive samples is a view; a re-ranged micro-batch is gathered (one small index copy per tensor)
@@ -139,6 +143,17 @@ def train_window(args, transformer, samples: Dict, advantages: torch.Tensor, sig
             step = int(perms[ids[0]][t]) if perms is not None else t               # TR:553
             lat = samples["latents"][sel, t]
             rows = stats_rows[sel] if isinstance(sel, slice) else torch.zeros(len(ids), 4, dtype=torch.float32, device=dev)
+            if dpm_all:
+                for i in ids:                                                        # the reference's B == 1 evaluation (TR:542-585)
+                    one = slice(i, i + 1)
+                    new_lp = grpo_one_step(args, samples["latents"][one, t], samples["next_latents"][one, t], encoder_hidden_states[one],
+                                           pooled_prompt_embeds[one], text_ids[one], image_ids, transformer, samples["timesteps"][one, t],
+                                           step, sigma_schedule)
+                    out = _grpo.grpo_loss(new_lp, samples["log_probs"][one, t], advantages[one], args.clip_range, args.adv_clip_max,
+                                          args.kl_coeff, args.gradient_accumulation_steps, T)
+                    out[0].backward()
+                    stats_rows[i] += torch.stack([o.detach() for o in out])
+                continue
             pred = _forward(transformer, lat, encoder_hidden_states[sel], pooled_prompt_embeds[sel], text_ids[sel], image_ids,
                             samples["timesteps"][sel, t])
             _, _, grad = _rollout.policy_update(pred, lat, samples["next_latents"][sel, t], samples["log_probs"][sel, t],

@@ -54,12 +54,12 @@ def test_host_side_argument_validation_needs_no_gpu():
     from mixgrpo_b200 import _cabi
     lib = _cabi.lib()
     k = _cabi.StepCoefs()
-    assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 256
+    assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 512
     assert lib.mixgrpo_step_workspace_bytes(0, 10) == 0
-    assert lib.mixgrpo_step_workspace_bytes(100, 10) == 1792
+    assert lib.mixgrpo_step_workspace_bytes(100, 10) == 3328
     # null pointers / bad sizes / bad enums are rejected with MIXGRPO_EINVAL before any launch
-    assert lib.mixgrpo_flow_step(None, 1, None, 0, None, None, 0, None, 0, None, None, None, None, 0, 1, 8, ctypes.byref(k), 0, 0, None) == -1
-    assert lib.mixgrpo_dpm_step(1, 1, 1, 8, None, None, None, 4, None, 8, None, None, None, None, 0, 1, 8, ctypes.byref(k), 2, 0, None) == -1
+    assert lib.mixgrpo_flow_step(None, 1, None, 0, None, None, 0, None, 0, None, None, None, None, 0, 1, 8, ctypes.byref(k), 0, 0, None, None) == -1
+    assert lib.mixgrpo_dpm_step(1, 1, 1, 8, None, None, None, 4, None, 8, None, None, None, None, 0, 1, 8, ctypes.byref(k), 2, 0, None, None) == -1
     assert lib.mixgrpo_logprob_bwd(7, 1, 1, 1, 8, 1, 8, 1, 1, 1, 8, ctypes.byref(k), 0, None) == -1
     assert lib.mixgrpo_group_advantages(None, None, 1, 4, 4, 0, 1, None, 0, None, None) == -1
     assert lib.mixgrpo_grpo_loss(None, None, None, 1, 1e-4, 5.0, 0.0, 12.0, None, None, None, None) == -1
@@ -128,11 +128,11 @@ int main(int argc, char** argv) {
   int64_t (*ws)(int64_t, int64_t) = (int64_t (*)(int64_t, int64_t))dlsym(h, "mixgrpo_step_workspace_bytes");
   int64_t (*rb)(int, int64_t) = (int64_t (*)(int, int64_t))dlsym(h, "mixgrpo_peer_region_bytes");
   int (*step)(const void*, int, const float*, int64_t, const void*, const float*, int64_t, float*, int64_t, float*, float*, float*, void*,
-              int64_t, int64_t, int64_t, const mixgrpo_step_coefs*, int, unsigned, void*) = dlsym(h, "mixgrpo_flow_step");
+              int64_t, int64_t, int64_t, const mixgrpo_step_coefs*, int, unsigned, void*, const mixgrpo_step_ext*) = dlsym(h, "mixgrpo_flow_step");
   mixgrpo_step_coefs k = {0};
   if (!abi || !ws || !rb || !step) return 3;
   printf("%d %lld %lld %d\n", abi(), (long long)ws(12, 262144), (long long)rb(8, 36),
-         step(NULL, MIXGRPO_BF16, NULL, 0, NULL, NULL, 0, NULL, 0, NULL, NULL, NULL, NULL, 0, 1, 8, &k, MIXGRPO_SRC_NOISE, 0u, NULL));
+         step(NULL, MIXGRPO_BF16, NULL, 0, NULL, NULL, 0, NULL, 0, NULL, NULL, NULL, NULL, 0, 1, 8, &k, MIXGRPO_SRC_NOISE, 0u, NULL, NULL));
   return abi() == MIXGRPO_ABI_VERSION ? 0 : 4;
 }
 ''')
@@ -143,7 +143,7 @@ int main(int argc, char** argv) {
     r = subprocess.run([str(exe), str(lib)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     abi, ws, rb, rc = r.stdout.split()
-    assert int(abi) == _cabi.ABI_VERSION and int(ws) == 256 and int(rb) == 256 + 2 * 8 * 36 * 8 + 2 * 8 * 256 * 8 and int(rc) == -1
+    assert int(abi) == _cabi.ABI_VERSION and int(ws) == 512 and int(rb) == 256 + 2 * 8 * 36 * 8 + 2 * 8 * 256 * 8 and int(rc) == -1
 
 
 def test_missing_library_fails_loudly_instead_of_falling_back(monkeypatch, tmp_path):

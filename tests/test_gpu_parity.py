@@ -236,13 +236,14 @@ def test_advantages_vs_oracle():
     from mixgrpo_b200 import grpo
     d = _dev()
     g = torch.Generator().manual_seed(1)
-    r = {"hps": torch.randn(24, generator=g), "pick": torch.randn(24, generator=g) * 0.02 + 0.3, "ir": torch.randn(24, generator=g)}
+    # BASELINE's synthetic inputs: 3 models x N(0,1) scores plus one constant group — at the 1e-6 gate
+    r = {"hps": torch.randn(24, generator=g), "pick": torch.randn(24, generator=g), "ir": torch.randn(24, generator=g)}
     r["ir"][12:] = 0.25                                           # a constant group (std = 0)
     w = {"hps": 1.0, "pick": 0.5, "ir": 2.0}
     for ratio in (0.0, 0.2, 0.5):
         got = grpo.compute_group_advantages({k: t.to(d) for k, t in r.items()}, 12, w, trimmed_ratio=ratio)
         ref = GO.group_advantages(r, 12, w, trimmed_ratio=ratio)
-        assert torch.allclose(got.cpu(), ref, rtol=1e-5, atol=2e-5), (ratio, (got.cpu() - ref).abs().max())
+        assert torch.allclose(got.cpu(), ref, rtol=1e-6, atol=1e-6), (ratio, (got.cpu() - ref).abs().max())
     single = torch.tensor([0.1, 0.4, 0.2, 0.9])
     got = grpo.compute_group_advantages(single.to(d), 4)
     assert torch.allclose(got.cpu(), GO.group_advantages(single, 4), atol=1e-6)
@@ -257,6 +258,54 @@ def test_advantages_vs_oracle():
     assert torch.allclose(got.cpu(), ref, atol=1e-6)
     with pytest.raises(ValueError):
         grpo.compute_group_advantages({k: t.to(d) for k, t in r.items()}, 12, w, use_group=False)
+
+
+def _assert_rows_at_gate(rows, ref_rows, new_lp, ref_lp, old_lp, denom):
+    """north_star gate: loss within 1e-4 relative.  Columns: loss, policy_loss, kl_loss, clip_frac (TR:575-583).
+    loss / policy_loss / clip_frac are asserted AT the gate.  kl_loss = 0.5 (new-old)^2/denom is a difference of nearly
+    equal log-probs squared: its sensitivity to the log-prob is |new-old|/denom, so it is held to the gate plus exactly
+    what the MEASURED log-prob deviation (itself asserted <= 1e-5 relative, gate 1e-4) propagates to."""
+    assert torch.allclose(rows[:, :2], ref_rows[:, :2], rtol=1e-4, atol=1e-7), (rows[:, :2] - ref_rows[:, :2]).abs().max()
+    assert torch.equal(rows[:, 3], ref_rows[:, 3])
+    dlp = (new_lp - ref_lp).abs()
+    kl_slack = ((ref_lp - old_lp).abs() + dlp) * dlp / denom
+    assert ((rows[:, 2] - ref_rows[:, 2]).abs() <= 1e-4 * ref_rows[:, 2].abs() + kl_slack + 1e-12).all(), (rows[:, 2], ref_rows[:, 2])
+
+
+def _adv_truth_fp64(r, G, w, trim):
+    """TR:439-468 in float64 on the same fp32 scores: the value both fp32 implementations approximate."""
+    out = torch.zeros(next(iter(r.values())).numel(), dtype=torch.float64)
+    for k, t in r.items():
+        t = t.double()
+        for s in range(0, t.numel(), G):
+            grp = t[s:s + G]
+            kept = torch.sort(grp).values[trim:] if trim else grp
+            out[s:s + G] += w[k] * (grp - kept.mean()) / (kept.std() + 1e-8)
+    return out
+
+
+@pytest.mark.parametrize("spread,offset", [(0.02, 0.3), (1e-3, 20.0), (5e-4, -3.0)])
+def test_advantages_ill_conditioned_groups_vs_fp64_truth(spread, offset):
+    """Tight groups (PickScore-like scores: sigma << |mean|) amplify the rounding of mean and std by |mean|/sigma, so two
+    correct fp32 implementations differ by more than the 1e-6 gate there.  The kernel takes the group statistics in fp64
+    (csrc/grpo_kernels.cu) where the reference uses fp32 mean()/std(): against the float64 truth it must be at least as
+    accurate as the reference's own fp32 path, and agree with the reference to within the reference's own error."""
+    from mixgrpo_b200 import grpo
+    d = _dev()
+    g = torch.Generator().manual_seed(5)
+    r = {"hps": torch.randn(24, generator=g), "pick": torch.randn(24, generator=g) * spread + offset, "ir": torch.randn(24, generator=g)}
+    w = {"hps": 1.0, "pick": 0.5, "ir": 2.0}
+    for ratio in (0.0, 0.2):
+        trim = min(int(12 * ratio), 11)
+        got = grpo.compute_group_advantages({k: t.to(d) for k, t in r.items()}, 12, w, trimmed_ratio=ratio).cpu().double()
+        ref = GO.group_advantages(r, 12, w, trimmed_ratio=ratio).double()
+        truth = _adv_truth_fp64(r, 12, w, trim)
+        err_kernel, err_ref = (got - truth).abs().max().item(), (ref - truth).abs().max().item()
+        # not worse than the reference's own fp32 path (both round mean / std to fp32, which costs eps*|mean|/sigma)
+        assert err_kernel <= 1.05 * err_ref + 5e-7, (ratio, err_kernel, err_ref)
+        if spread / abs(offset) > 0.05:                                                  # PickScore-like: still at the gate vs the truth
+            assert err_kernel <= 1e-6, (ratio, err_kernel)
+        assert (got - ref).abs().max().item() <= err_ref + err_kernel + 1e-9
 
 
 @pytest.mark.parametrize("kl", [0.0, 0.01])
@@ -343,7 +392,7 @@ def test_fused_policy_update_vs_oracle_autograd(dtype, flow):
         ref_rows[i] = torch.stack([o.detach() for o in out])
         lps.append(lp.detach())
     assert torch.allclose(new_lp.cpu(), torch.cat(lps), rtol=1e-5, atol=0)
-    assert torch.allclose(rows.cpu(), ref_rows, rtol=2e-4, atol=1e-7), (rows.cpu() - ref_rows).abs().max()
+    _assert_rows_at_gate(rows.cpu(), ref_rows, new_lp.cpu(), torch.cat(lps), old_lp, GA * T)
     assert gv.dtype == dtype
     tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
     assert _rel(gv.float().cpu(), vc.grad.float()) < tol

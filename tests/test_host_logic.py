@@ -184,3 +184,23 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0 and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("shift", [1.0, 2.0, 3.0, 5.0])
+def test_train_timesteps_use_fp32_product_like_the_reference(shift):
+    """TR:401 / SU:63-65: ``int(sigma * 1000)`` on an fp32 0-dim tensor.  A python-double product is off by one for many
+    (N, shift) pairs (e.g. N=20, shift=3 -> 899 vs 900 at i=5), which would make the policy update evaluate the DiT at a
+    different timestep than the rollout did."""
+    differs_from_double = 0
+    for n in range(4, 51):
+        sig = O.sd3_time_shift(shift, torch.linspace(1, 0, n + 1))
+        ref = [int(s * 1000) for s in sig][:n]                                  # the reference expression, verbatim
+        assert R.timestep_values(sig, n) == ref
+        host = coefs.host_schedule(sig)
+        assert [int(host[i] * 1000) for i in range(n)] == ref                   # what run_sample_step feeds the transformer
+        differs_from_double += [int(s * 1000) for s in sig.tolist()][:n] != ref
+        x = torch.zeros(2, n + 1, 1, 64)
+        smp = R.make_samples(x, torch.zeros(2, n), sig, n)
+        assert smp["timesteps"].tolist() == [ref[:-1]] * 2
+    if shift in (1.0, 3.0):
+        assert differs_from_double > 0                                          # the sweep does cover the off-by-one cases

@@ -59,7 +59,7 @@ def main():
         rc = lib.mixgrpo_flow_step(vs[i].data_ptr(), 1, xs[i].data_ptr(), n, es[i].data_ptr() if src == SRC_NOISE else None,
                                    outs[(i + 1) % ns].data_ptr() if src == SRC_GIVEN else None, n,
                                    outs[i].data_ptr() if src != SRC_GIVEN else None, n, x0s[i].data_ptr() if x0 else None, None,
-                                   lp.data_ptr(), ws.data_ptr(), ws.numel(), B, n, C.byref(k), src, flags, st)
+                                   lp.data_ptr(), ws.data_ptr(), ws.numel(), B, n, C.byref(k), src, flags, st, None)
         assert rc == 0, rc
 
     def bwd(i):
