@@ -81,8 +81,8 @@ __device__ __forceinline__ void store_decoded(const StepParams& p, int b, long l
 //   whose returned count is the last one owns the complete sum in (old + mine), writes
 //   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
 //   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2).  A share too large for the field (> 255/ctas)
-//   goes into the record's 64-bit side accumulator instead (packed_share / packed_total in step_math.cuh), so the
-//   log-prob stays finite like the reference's up to |d|/s ~ 16000; only a non-finite share gives NaN.
+//   goes into the record's 64-bit side accumulators instead (packed_share / packed_total in step_math.cuh), so the
+//   log-prob stays finite like the reference's up to |d|/s ~ 4e7; only a non-finite share (or one beyond that) gives NaN.
 
 template <class T, bool VECTOR>
 __device__ __forceinline__ void load_tile(const T* base, long long off, long long n, float (&r)[kVec]) {

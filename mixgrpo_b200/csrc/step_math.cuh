@@ -18,20 +18,25 @@ constexpr int kMaxCtasPerSample = (1 << kCountBits) - 1;
 // — see mixgrpo_step_workspace_bytes
 constexpr int kWsStride = 4;
 constexpr int kWsWide = 2;                      // word index of the side accumulator inside a record
-constexpr float kWideCap = 134217728.f;         // 2^27: largest per-CTA share the side accumulator takes (4095 CTAs x 2^27 x 2^24 < 2^63)
+constexpr int kWsHuge = 3;                      // word index of the second side accumulator (integer units)
+constexpr float kWideCap = 134217728.f;         // 2^27: largest per-CTA share the Q39.24 side accumulator takes (4095 CTAs x 2^27 x 2^24 < 2^63)
+constexpr float kHugeCap = 1125899906842624.f;  // 2^50: largest share the integer side accumulator takes (4095 x 2^50 < 2^63)
 
 // The packed word holds shares of mean(d^2 / 2 s^2) up to 255/ctas each — ample for any transition a sane policy
 // produces (the value is ~0.5 on the rollout's own samples).  The reference, though, returns a FINITE log-prob however far
 // x_next is from the mean (SU:201-208), so a share that does not fit is not dropped: it goes, as Q39.24 fixed point, into
 // the record's 64-bit side accumulator (integer adds: still order-independent, still bitwise reproducible) and the CTA
 // only flags the fact in the packed word's 12-bit "wide" count.  The finalizer — the CTA that sees the last arrival —
-// folds the side word in and re-zeroes it.  Only a non-finite / negative share, or one above 2^27 (|d|/s > 16000),
-// yields NaN.  The common path is unchanged: one atomicAdd per CTA, no fence.
+// folds the side word in and re-zeroes it.  A share above 2^27 (|d|/s > 16000) goes, rounded to an integer (relative
+// resolution 2^-27), into a second side word; only a non-finite / negative share, or one above 2^50 (|d|/s > 4e7, where
+// the reference's own fp32 mean has long lost its digits), yields NaN.  The common path is unchanged: one atomicAdd per
+// CTA, no fence.
 __device__ __forceinline__ unsigned long long packed_share(float r, int ctas, unsigned long long* rec) {
   const float cap = 255.0f / (float)ctas;
   unsigned long long add = 1ull;
   if (!(r >= 0.f && r <= cap)) {
     if (r > cap && r <= kWideCap) atomicAdd(rec + kWsWide, __float2ull_rn(r * 16777216.0f));
+    else if (r > kWideCap && r <= kHugeCap) atomicAdd(rec + kWsHuge, __float2ull_rn(r));
     else atomicOr(rec + kWsWide, 1ull << 63);
     __threadfence();                             // the side word is visible before this CTA's arrival is counted
     add += 1ull << kCountBits;
@@ -46,8 +51,9 @@ __device__ __forceinline__ float packed_total(unsigned long long tot, unsigned l
   if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) {
     __threadfence();
     const unsigned long long wide = atomicExch(rec + kWsWide, 0ull);      // read and leave zeroed for the next launch
+    const unsigned long long huge = atomicExch(rec + kWsHuge, 0ull);
     if (wide >> 63) return __int_as_float(0x7fc00000);
-    q += (double)wide * (1.0 / 16777216.0);
+    q += (double)wide * (1.0 / 16777216.0) + (double)huge;
   }
   return (float)q;
 }

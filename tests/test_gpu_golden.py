@@ -62,7 +62,7 @@ def test_flow_and_dance_vs_reference_cpu_golden(dn, dtype):
         out = su.dance_grpo_step(v, x, ETA, SIG, idx, None, True, bool(sde), noise=_t(z[f"{k}/noise"]).to(DEV), rounding="ref_cpu")
         assert _eq(out[0], _t(z[f"{k}/prev"])) and _eq(out[1], _t(z[f"{k}/x0"])), k
         assert torch.allclose(out[2].cpu(), _t(z[f"{k}/logp"]), rtol=1e-4, atol=1e-12)
-        vg = v.clone().requires_grad_(True)
+        vg = v.clone().requires_grad_(bool(sde))        # sde_solver=False has no backward kernel (never trained, TR:159-168): it raises
         lp = su.dance_grpo_step(vg, x, ETA, SIG, idx, _t(z[f"{k}/xn_train"]).to(DEV), True, bool(sde), rounding="ref_cpu")[2]
         assert _close(lp, _t(z[f"{k}/train_logp"]), 1e-4)
         if sde:
