@@ -25,7 +25,10 @@ UNIT_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):                      # a raw page exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > X.csv
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out[out.index('"ID"'):])))
     hdr, units = rows[0], rows[1]
     return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
