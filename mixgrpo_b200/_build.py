@@ -79,5 +79,54 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+# ------------------------------------------------------------------------------------------ compiled Python binding
+BIND_SRC = PKG / "csrc_bind" / "torch_bind.cpp"
+BIND_LIB = LIBDIR / "_torchbind.so"
+BIND_STAMP = LIBDIR / "_torchbind.stamp"
+
+
+def _bind_hash() -> str:
+    import torch
+    h = hashlib.sha256()
+    h.update(BIND_SRC.read_bytes())
+    h.update((INCLUDE / "mixgrpo_b200.h").read_bytes())
+    h.update(torch.__version__.encode())
+    h.update(sys.version.encode())
+    return h.hexdigest()
+
+
+def binding_is_fresh() -> bool:
+    return BIND_LIB.exists() and BIND_STAMP.exists() and BIND_STAMP.read_text().strip() == _bind_hash()
+
+
+def build_binding(force: bool = False, verbose: bool = False) -> Path:
+    """g++ -shared of csrc_bind/torch_bind.cpp against libtorch / libtorch_python and the in-tree libmixgrpo_b200.so
+    (rpath $ORIGIN): the pybind11 + torch::autograd layer over the SAME C ABI the ctypes binding calls.  In-tree and
+    stamp-guarded like the CUDA library (no JIT cache: the built .so travels with the gpurun snapshot)."""
+    if not force and binding_is_fresh():
+        return BIND_LIB
+    build()                                              # the library it links against
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cuda_home = Path(_nvcc()).resolve().parent.parent
+    inc = [*ce.include_paths(), sysconfig.get_paths()["include"], str(cuda_home / "include"), str(INCLUDE)]
+    torch_lib = str(Path(torch.__file__).resolve().parent / "lib")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_torchbind", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", *[f"-I{i}" for i in inc], str(BIND_SRC), "-o", str(BIND_LIB),
+           f"-L{LIBDIR}", "-lmixgrpo_b200", f"-L{torch_lib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{torch_lib}"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {BIND_SRC.name}:\n{r.stdout}\n{r.stderr}")
+    BIND_STAMP.write_text(_bind_hash() + "\n")
+    return BIND_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_binding(force="--force" in sys.argv, verbose=True))

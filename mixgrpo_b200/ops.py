@@ -7,6 +7,7 @@ is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -21,6 +22,39 @@ _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 #: number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
 launch_count = 0
+
+_binding_mod = None
+_binding_tried = False
+
+
+def binding():
+    """The compiled binding ``_lib/_torchbind.so`` (csrc_bind/torch_bind.cpp: pybind11 + torch::autograd over the SAME C ABI)
+    or ``None`` — then every call goes through ctypes (``_cabi``), which is only a slower way to reach the same entry points.
+    ``MIXGRPO_BINDING=ctypes`` forces that; a missing / stale binding is rebuilt when a C++ compiler is here (one minute)
+    unless ``MIXGRPO_NO_REBUILD=1``."""
+    global _binding_mod, _binding_tried
+    if _binding_tried:
+        return _binding_mod
+    _binding_tried = True
+    if os.environ.get("MIXGRPO_BINDING", "compiled") == "ctypes":
+        return None
+    from . import _build
+    _cabi.lib()                                           # libmixgrpo_b200.so first: the binding links against it
+    try:
+        if not _build.binding_is_fresh() and os.environ.get("MIXGRPO_NO_REBUILD") != "1":
+            _build.build_binding()
+        if _build.BIND_LIB.exists():
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_torchbind", str(_build.BIND_LIB))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            if mod.abi_version() == _cabi.ABI_VERSION:
+                _binding_mod = mod
+    except Exception as e:  # noqa: BLE001  (no compiler / torch headers: the ctypes loader still reaches every kernel)
+        import warnings
+        warnings.warn(f"mixgrpo_b200: compiled binding unavailable ({type(e).__name__}: {e}); using the ctypes loader")
+        _binding_mod = None
+    return _binding_mod
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -159,6 +193,25 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     ``decode``: ``{"out": fp32 (B,C,H,W), "divisor": 0.3611, "shift": 0.1159, "from_x0": False, "reciprocal": False}`` —
     the VAE's input (unpack + de-normalise, TR:102-115, TR:286-287) written by this launch as a second output."""
     global launch_count
+    tb = binding()
+    if tb is not None:                                    # compiled binding: same checks, same C-ABI call, no interpreter time
+        has_ph, seed, off, state = False, 0, 0, 0
+        if src == SRC_PHILOX and philox is not None:
+            has_ph = True
+            if isinstance(philox[0], PhiloxState):
+                off, state = int(philox[1]) & 0xFFFFFFFFFFFFFFFF, philox[0].state.data_ptr()
+            else:
+                seed, off = int(philox[0]) & 0xFFFFFFFFFFFFFFFF, int(philox[1]) & 0xFFFFFFFFFFFFFFFF
+        if decode is None:
+            res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
+                                want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, None, 1.0, 0.0, False, False)
+        else:
+            res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
+                                want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, decode["out"],
+                                float(decode.get("divisor", 1.0)), float(decode.get("shift", 0.0)), bool(decode.get("from_x0", False)),
+                                bool(decode.get("reciprocal", False)))
+        launch_count += 1
+        return res
     lib = _cabi.lib()
     _require_cuda(v, "model_output")
     _require_cuda(x, "latents")
@@ -283,6 +336,10 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
                      coefs: StepCoefs, round_like_torch: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """grad of sum_b grad_logp[b]*logp[b] w.r.t. model_output; dtype = model_output.dtype."""
     global launch_count
+    tb = binding()
+    if tb is not None:
+        launch_count += 1
+        return tb.logprob_backward(family, v, x, x_next, grad_logp, C.addressof(coefs), round_like_torch, out)
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (grad_logp, "grad_log_prob")):
         _require_cuda(t, nm)
@@ -336,6 +393,11 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
     """Fused policy-update forward (mixgrpo_policy_fwd): new log-probs [B]; per-sample loss terms += stats_rows.
     ``early_loads``: no input tensor was written by the launch immediately before this one on the stream."""
     global launch_count
+    tb = binding()
+    if tb is not None:
+        launch_count += 1
+        return tb.policy_forward(family, v, x, x_next, C.addressof(coefs), old_logp, advantages, float(clip_range), float(adv_clip_max), float(kl_coeff),
+                                 float(denom), stats_rows, round_like_torch, out_logp, accumulate, early_loads)
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample")):
         _require_cuda(t, nm)
@@ -366,6 +428,11 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     ``early_loads``: the caller launched ``policy_forward`` on the same inputs immediately before (nothing in between
     writes v / x / x_next), so the kernel may load them while that launch drains (MIXGRPO_FLAG_PDL_EARLY_LOADS)."""
     global launch_count
+    tb = binding()
+    if tb is not None:
+        launch_count += 1
+        return tb.policy_backward(family, v, x, x_next, new_logp, C.addressof(coefs), old_logp, advantages, float(clip_range), float(adv_clip_max),
+                                  float(kl_coeff), float(denom), round_like_torch, early_loads)
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (new_logp, "new_log_probs")):
         _require_cuda(t, nm)

@@ -173,17 +173,21 @@ class PeerExchange:
         return adv, gathered
 
     def allreduce_stats(self, values: torch.Tensor, average: bool = True) -> torch.Tensor:
-        """In-place sum (in rank order — same bits on every rank) or average of ``values`` (fp32, <= 256 entries) over
-        the ranks: the ONE reduction per ``train_one_step`` that replaces TR:586-600's four all-reduce + ``.item()``
-        pairs per (sample, window step)."""
+        """In-place sum (in rank order — same bits on every rank) or average of ``values`` (contiguous fp32) over the ranks:
+        the ONE reduction per ``train_one_step`` that replaces TR:586-600's four all-reduce + ``.item()`` pairs per (sample,
+        window step).  One launch per 256 entries (the kernel's message size); the usual [4] or [window, B, 4] sums are one."""
         _ops._require_cuda(values, "values")
-        if values.dtype != torch.float32 or not values.is_contiguous() or values.numel() < 1 or values.numel() > 256:
-            raise ValueError("mixgrpo_b200: allreduce_stats takes a contiguous fp32 tensor of 1..256 entries")
+        if values.dtype != torch.float32 or not values.is_contiguous() or values.numel() < 1:
+            raise ValueError("mixgrpo_b200: allreduce_stats takes a contiguous fp32 tensor with at least one entry")
+        flat = values.view(-1)
         with torch.cuda.device(values.device):
-            rc = self._lib.mixgrpo_peer_allreduce(self._regions_c, self.rank, self.world, self.cap, values.data_ptr(), values.numel(),
-                                                  1 if average else 0, _ops._stream_ptr(values.device))
-        _cabi.check(rc, "peer_allreduce")
-        _ops.launch_count += 1
+            st = _ops._stream_ptr(values.device)
+            for lo in range(0, flat.numel(), 256):
+                cnt = min(256, flat.numel() - lo)
+                rc = self._lib.mixgrpo_peer_allreduce(self._regions_c, self.rank, self.world, self.cap, flat.data_ptr() + 4 * lo, cnt,
+                                                      1 if average else 0, st)
+                _cabi.check(rc, "peer_allreduce")
+                _ops.launch_count += 1
         return values
 
     # ------------------------------------------------------------------ introspection / teardown

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import math
 import os
+from ctypes import addressof as _addressof
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -131,6 +132,16 @@ class _TransitionLogProb(torch.autograd.Function):
         return grad_v, None, None, None, None, None, None
 
 
+def _transition_logprob(v, x, x_next, k, family, rnd, want_mean):
+    """Differentiable stored-transition log-prob: the C++ ``torch::autograd::Function`` of the compiled binding (forward and
+    backward never re-enter the interpreter) or, through the ctypes loader, the Python ``autograd.Function`` above."""
+    tb = _ops.binding()
+    if tb is not None:
+        _ops.launch_count += 1                                          # forward; the backward launch is counted when it runs... in C++
+        return tb.transition_logprob(v, x, x_next, _addressof(k), family, rnd, want_mean)
+    return _TransitionLogProb.apply(v, x, x_next, k, family, rnd, want_mean)
+
+
 def flow_grpo_step(
     model_output: torch.Tensor,
     latents: torch.Tensor,
@@ -187,7 +198,7 @@ def flow_grpo_step(
                                              want_mean=return_mean, round_like_torch=rnd)
         return xn, x0, logp, mean, scale_t
     if torch.is_grad_enabled() and model_output.requires_grad:
-        logp, x0, mean = _TransitionLogProb.apply(model_output, latents, prev_sample, k, _ops.FLOW, rnd, return_mean)
+        logp, x0, mean = _transition_logprob(model_output, latents, prev_sample, k, _ops.FLOW, rnd, return_mean)
         return prev_sample, x0, logp, (mean if return_mean else None), scale_t
     xn, x0, logp, mean = _ops.fused_step(_ops.FLOW, model_output, latents, k, src=SRC_GIVEN, x_next=prev_sample,
                                          want_mean=return_mean, round_like_torch=rnd)
@@ -233,7 +244,7 @@ def dance_grpo_step(
                                               sde_solver=False, round_like_torch=rnd)
         return xn, x0, logp
     if torch.is_grad_enabled() and model_output.requires_grad and sde_solver:
-        logp, x0, _ = _TransitionLogProb.apply(model_output, latents, prev_sample, k, _ops.DANCE, rnd, False)
+        logp, x0, _ = _transition_logprob(model_output, latents, prev_sample, k, _ops.DANCE, rnd, False)
         return prev_sample, x0, logp
     xn, x0, logp, _ = _ops.fused_step(_ops.DANCE, model_output, latents, k, src=SRC_GIVEN, x_next=prev_sample,
                                       sde_solver=sde_solver, round_like_torch=rnd)

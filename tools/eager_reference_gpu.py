@@ -12,7 +12,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from mixgrpo_b200 import sampling_utils as su  # noqa: E402
+from mixgrpo_b200 import ops, sampling_utils as su  # noqa: E402
 from oracle import ref_loader, sampling_oracle as O  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -61,10 +61,26 @@ for B in (1, 12):
         lp.sum().backward()
         return vg.grad
 
+    def our_train_fused():
+        # the policy update as the trainer issues it (rollout.policy_update): forward + loss and backward, no autograd at all
+        k = our_train_fused.k
+        nl = ops.policy_forward(ops.FLOW, v, x, xn, k, old, adv, 1e-4, 5.0, 0.01, 12.0, round_like_torch=True)
+        return ops.policy_backward(ops.FLOW, v, x, xn, nl, k, old, adv, 1e-4, 5.0, 0.01, 12.0, round_like_torch=True, early_loads=True)
+
+    from mixgrpo_b200 import coefs
+    our_train_fused.k = coefs.flow(sig, 9, ETA, "ref_cuda", True)[0]
+    old = torch.randn(B, device=dev) * 0.01 - 1
+    adv = torch.randn(B, device=dev)
     rows["reference eager: rollout SDE step + log-prob"] = timed(ref_rollout)
-    rows["mixgrpo_b200:    rollout SDE step + log-prob (drop-in, 1 launch)"] = timed(lambda: su.flow_grpo_step(v, x, ETA, sig, 9, None, noise=eps, return_mean=False))
     rows["reference eager: log-prob forward + autograd backward"] = timed(ref_train)
-    rows["mixgrpo_b200:    log-prob forward + closed-form backward (autograd.Function, 2 launches)"] = timed(our_train)
+    compiled = ops.binding()
+    for loader in (["compiled binding"] if compiled is not None else []) + ["ctypes loader"]:
+        ops._binding_mod = compiled if loader == "compiled binding" else None
+        rows[f"mixgrpo_b200 [{loader}]: rollout SDE step + log-prob (drop-in flow_grpo_step, 1 launch)"] = timed(lambda: su.flow_grpo_step(v, x, ETA, sig, 9, None, noise=eps, return_mean=False))
+        rows[f"mixgrpo_b200 [{loader}]: drop-in flow_grpo_step, full 5-tuple (mean written too)"] = timed(lambda: su.flow_grpo_step(v, x, ETA, sig, 9, None, noise=eps))
+        rows[f"mixgrpo_b200 [{loader}]: log-prob forward + closed-form backward through autograd (lp.sum().backward(), 2 launches + torch's sum/backward)"] = timed(our_train)
+        rows[f"mixgrpo_b200 [{loader}]: fused policy forward + backward (ops.policy_forward / policy_backward, 2 launches, no autograd)"] = timed(our_train_fused)
+    ops._binding_mod = compiled
     for k, (dev_us, wall_us) in rows.items():
         print(json.dumps({"B": B, "what": k, "us_per_call_cuda_events": round(dev_us, 1), "us_per_call_wall": round(wall_us, 1),
                           "reference_impl": "unmodified reference file" if ref is not None else "oracle restatement"}), flush=True)
