@@ -77,6 +77,7 @@ void check_rc(int rc, const char* what) {
 // one zero-initialised workspace per (device, stream): the kernels leave the records zeroed, so it is reused by every
 // launch on that stream; never cached when allocated inside a CUDA-graph capture (its memory belongs to the graph's pool)
 std::unordered_map<uint64_t, Tensor> g_workspaces;
+int64_t g_autograd_backward_launches = 0;   // launches issued from TransitionLogProb::backward (the interpreter never sees them)
 
 Tensor workspace(const c10::Device& dev, int64_t B, int64_t n, cudaStream_t st) {
   const int64_t need = mixgrpo_step_workspace_bytes(B, n);
@@ -288,6 +289,7 @@ struct TransitionLogProb : public torch::autograd::Function<TransitionLogProb> {
       std::memcpy(&k, raw.data(), sizeof(k));
       grad_v = logprob_backward_impl((int)ctx->saved_data["family"].toInt(), saved[0], saved[1], saved[2], grads[0], k, ctx->saved_data["rnd"].toBool(),
                                      c10::nullopt);
+      if (saved[0].size(0) > 0) ++g_autograd_backward_launches;
     }
     return {grad_v, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
   }
@@ -330,6 +332,7 @@ LossArgsIn loss_args(const Tensor& old_logp, const Tensor& advantages, const Opt
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "compiled binding of include/mixgrpo_b200.h's hot entry points (same C ABI as the ctypes layer)";
   m.def("abi_version", []() { return mixgrpo_abi_version(); });
+  m.def("autograd_backward_launches", []() { return g_autograd_backward_launches; });
 
   m.def("fused_step",
         [](int family, const Tensor& v, const Tensor& x, uint64_t coefs_addr, int src, const OptT& noise, const OptT& x_next, const OptT& m1, const OptT& m2,

@@ -57,6 +57,12 @@ def binding():
     return _binding_mod
 
 
+def total_launches() -> int:
+    """``launch_count`` plus the backward launches the compiled binding's C++ autograd Function issued (those never pass
+    through this module)."""
+    return launch_count + (_binding_mod.autograd_backward_launches() if _binding_mod is not None else 0)
+
+
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
         raise RuntimeError(f"mixgrpo_b200: `{name}` must be a CUDA tensor — this package has no CPU fallback "
@@ -210,7 +216,7 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                                 want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, decode["out"],
                                 float(decode.get("divisor", 1.0)), float(decode.get("shift", 0.0)), bool(decode.get("from_x0", False)),
                                 bool(decode.get("reciprocal", False)))
-        launch_count += 1
+        launch_count += 1 if v.shape[0] else 0
         return res
     lib = _cabi.lib()
     _require_cuda(v, "model_output")
@@ -338,7 +344,7 @@ def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torc
     global launch_count
     tb = binding()
     if tb is not None:
-        launch_count += 1
+        launch_count += 1 if v.shape[0] else 0
         return tb.logprob_backward(family, v, x, x_next, grad_logp, C.addressof(coefs), round_like_torch, out)
     lib = _cabi.lib()
     for t, nm in ((v, "model_output"), (x, "latents"), (x_next, "prev_sample"), (grad_logp, "grad_log_prob")):
@@ -395,7 +401,7 @@ def policy_forward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.
     global launch_count
     tb = binding()
     if tb is not None:
-        launch_count += 1
+        launch_count += 1 if v.shape[0] else 0
         return tb.policy_forward(family, v, x, x_next, C.addressof(coefs), old_logp, advantages, float(clip_range), float(adv_clip_max), float(kl_coeff),
                                  float(denom), stats_rows, round_like_torch, out_logp, accumulate, early_loads)
     lib = _cabi.lib()
@@ -430,7 +436,7 @@ def policy_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch
     global launch_count
     tb = binding()
     if tb is not None:
-        launch_count += 1
+        launch_count += 1 if v.shape[0] else 0
         return tb.policy_backward(family, v, x, x_next, new_logp, C.addressof(coefs), old_logp, advantages, float(clip_range), float(adv_clip_max),
                                   float(kl_coeff), float(denom), round_like_torch, early_loads)
     lib = _cabi.lib()

@@ -137,7 +137,7 @@ def _transition_logprob(v, x, x_next, k, family, rnd, want_mean):
     backward never re-enter the interpreter) or, through the ctypes loader, the Python ``autograd.Function`` above."""
     tb = _ops.binding()
     if tb is not None:
-        _ops.launch_count += 1                                          # forward; the backward launch is counted when it runs... in C++
+        _ops.launch_count += 1 if v.shape[0] else 0                     # the forward; C++ counts its own backward launches (ops.total_launches)
         return tb.transition_logprob(v, x, x_next, _addressof(k), family, rnd, want_mean)
     return _TransitionLogProb.apply(v, x, x_next, k, family, rnd, want_mean)
 

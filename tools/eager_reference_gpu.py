@@ -71,8 +71,16 @@ for B in (1, 12):
     our_train_fused.k = coefs.flow(sig, 9, ETA, "ref_cuda", True)[0]
     old = torch.randn(B, device=dev) * 0.01 - 1
     adv = torch.randn(B, device=dev)
+    def autograd_floor():
+        # what torch itself charges for the same call pattern with a trivial built-in op in place of ours
+        vg = v.detach().requires_grad_(True)
+        lp = vg.mean(dim=(1, 2))
+        lp.sum().backward()
+        return vg.grad
+
     rows["reference eager: rollout SDE step + log-prob"] = timed(ref_rollout)
     rows["reference eager: log-prob forward + autograd backward"] = timed(ref_train)
+    rows["torch autograd floor: v.detach().requires_grad_(); v.mean((1,2)).sum().backward() (no mixgrpo code)"] = timed(autograd_floor)
     compiled = ops.binding()
     for loader in (["compiled binding"] if compiled is not None else []) + ["ctypes loader"]:
         ops._binding_mod = compiled if loader == "compiled binding" else None
