@@ -166,8 +166,19 @@ def test_allreduce_rank_order_sum_is_bitwise_reproducible(world, short_timeout):
             res = _run_all(eps, lambda e, r: e.allreduce_stats(on_dev[r], average=avg))
             for out in res:
                 assert torch.equal(out.cpu(), want), call
+        # longer vectors travel as 256-entry messages (one launch each): [4 x 24 x 4] stats rows of a group-24 window
+        vals = [torch.randn(4, 24, 4, generator=g) * (r + 1) for r in range(world)]
+        want = vals[0].clone()
+        for q in range(1, world):
+            want = want + vals[q]
+        on_dev = [v.to(dev) for v in vals]
+        torch.cuda.synchronize()
+        for out in _run_all(eps, lambda e, r: e.allreduce_stats(on_dev[r], average=False)):
+            assert torch.equal(out.cpu(), want)
         with pytest.raises(ValueError):
-            eps[0].allreduce_stats(torch.zeros(257, device=dev))
+            eps[0].allreduce_stats(torch.zeros(0, device=dev))
+        with pytest.raises(ValueError):
+            eps[0].allreduce_stats(torch.zeros(8, device=dev, dtype=torch.float64))
     finally:
         for e in eps:
             e.close()
