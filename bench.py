@@ -552,9 +552,18 @@ def e2e_run(w: Workload, steps: int, warmup: int, chunks: int, ref_out):
         st["evs"] = None
         return float(h_stats.sum(dim=(0, 1))[0])
 
-    # checked step: host inputs + the graph leg's noise -> the graph leg's outputs, bitwise
+    # checked step: host inputs + the graph leg's noise -> the graph leg's outputs, bitwise.  At N > 1 the graph leg's stats
+    # rows were rank-averaged in place by the logging reduction, so this step's rows go through the same reduction first.
     one(0, prefetch_next=False, eps=w.eps)
-    check = {"e2e_logp_equal": bool(torch.equal(h_lp, ref_out["logps"])), "e2e_stats_equal": bool(torch.equal(h_stats, ref_out["stats"]))}
+    got_stats = h_stats.clone()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        red = w.stats_rows.clone()
+        if w.px is not None:
+            w.px.allreduce_stats(red)
+        else:
+            dist.all_reduce(red, op=dist.ReduceOp.AVG)
+        got_stats = red.cpu()
+    check = {"e2e_logp_equal": bool(torch.equal(h_lp, ref_out["logps"])), "e2e_stats_equal": bool(torch.equal(got_stats, ref_out["stats"]))}
     for k in range(warmup):
         one(k, prefetch_next=k + 1 < warmup)
     torch.cuda.synchronize(w.dev)
@@ -776,10 +785,11 @@ def run_native(args):
     e2e_s = max(e2e_rank)
     e2e_value = total_bytes / e2e_s / 1e9
     ceil_rank = per_rank(h2d_ceiling(dev, h2d), dev)
-    ok = torch.tensor([1.0 if (e2e_check["e2e_logp_equal"] and e2e_check["e2e_stats_equal"]) else 0.0], device=dev)
+    ok = torch.tensor([1.0 if e2e_check["e2e_logp_equal"] else 0.0, 1.0 if e2e_check["e2e_stats_equal"] else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    check.update({"e2e_loss": e2e_loss, "e2e_logp_equal": bool(ok.item() == 1.0), "e2e_what": "one untimed e2e step on the graph leg's inputs and noise reproduces its log-probs and stats rows bitwise (every rank)"})
+    check.update({"e2e_loss": e2e_loss, "e2e_logp_equal": bool(ok[0].item() == 1.0), "e2e_stats_equal": bool(ok[1].item() == 1.0),
+                  "e2e_what": "one untimed e2e step on the graph leg's inputs and noise reproduces its log-probs and (rank-averaged) stats rows bitwise, on every rank"})
 
     # BASELINE configs[3] / configs[4] as whole-step lines at the same N (each: own graph, 3 warm-ups, CUDA events, max over ranks)
     configs = None
@@ -808,7 +818,7 @@ def run_native(args):
         cpu = cpu_reference_step(None, 1, budget_s=12.0)
     failed = world > 1 and not (check["gathered_equal"] and check["allreduce_equal"] and check["peer_adv_max_abs_err"] == 0.0
                                 and check["split_adv_max_abs_err"] <= 1e-6 and check["step_adv_max_abs_err"] == 0.0)
-    failed = failed or not check["e2e_logp_equal"]
+    failed = failed or not (check["e2e_logp_equal"] and check["e2e_stats_equal"])
     if rank == 0:
         coll = ("none (N=1)" if world == 1 else
                 "fused peer-memory kernels inside the step graph, no NCCL: reward gather + advantages (1 launch; 64-bit {call,value} words pushed into the peers' memory over NVLink), "
