@@ -375,13 +375,18 @@ def run_sample_step(
     *,
     noises: Optional[list] = None,
     rounding: Optional[str] = None,
+    decode: Optional[dict] = None,
 ):
     """SU:12-155 — the rollout loop: per step one transformer forward (opaque callable, bf16 autocast)
     and ONE fused sampler-step kernel that writes the next latent straight into its slot of the
     ``all_latents (B, N+1, S, 64)`` fp32 trajectory buffer (the reference appends to a list and pays a
     ``torch.stack`` copy at SU:153).  Returns ``(z, latents, all_latents, all_log_probs)``.
 
-    ``noises`` (keyword-only, optional): per-step explicit noise tensors (entries may be None)."""
+    ``noises`` (keyword-only, optional): per-step explicit noise tensors (entries may be None).
+    ``decode`` (keyword-only, optional): ``{"height": h, "width": w, "vae_scale_factor": 8, "divisor": 0.3611, "shift": 0.1159,
+    "reciprocal": True}`` — the LAST sampler step also writes the VAE's input ``unpack_latents(latents, h, w, 8) / 0.3611 +
+    0.1159`` (TR:102-115, TR:286-287) as a second output, returned in ``decode["out"]`` (fp32 (B, 16, h/8, w/8)): the unpack
+    launch and one read + write of the final latent disappear."""
     flash = False
     dpm_state = None
     last_sde = None
@@ -406,7 +411,15 @@ def run_sample_step(
     pred_original = None
     cur = z
     steps_done = 0
+    dec_last = None
+    if decode is not None:
+        vsf = int(decode.get("vae_scale_factor", 8))
+        hh, ww = 2 * (int(decode["height"]) // (vsf * 2)), 2 * (int(decode["width"]) // (vsf * 2))
+        decode["out"] = torch.empty((B, z.shape[-1] // 4, hh, ww), dtype=torch.float32, device=dev)
+        dec_last = {"out": decode["out"], "divisor": decode.get("divisor", 1.0), "shift": decode.get("shift", 0.0),
+                    "from_x0": bool(args.drop_last_sample), "reciprocal": bool(decode.get("reciprocal", False))}
     for i in progress_bar:
+        dec = dec_last if i == n_steps - 1 else None
         timestep_value = int(host_sig[i] * 1000)                                  # SU:63-65 without the sync
         timesteps = torch.full([encoder_hidden_states.shape[0]], timestep_value, device=dev, dtype=torch.long)
         transformer.eval()
@@ -438,19 +451,19 @@ def run_sample_step(
                 nz = torch.randn(pred.shape, device=dev, dtype=torch.float32)
             _, pred_original, lp, _ = _ops.fused_step(_ops.DPM, pred, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
                                                       noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
-                                                      out_logp=logps_t[i], round_like_torch=rnd)
+                                                      out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
             dpm_state.update(pred_original)
             dpm_state.update_lower_order()
         elif args.flow_grpo_sampling:
             k, _ = _coefs.flow(sigma_schedule, i, args.eta, mode, bf16_v)
             if determistic[i]:
                 _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_DETERMINISTIC, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd)
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
             else:
                 if nz is None:
                     nz = torch.randn(pred.shape, device=dev, dtype=pred.dtype)
                 _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_NOISE, noise=nz, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd)
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
             if flash:                                                               # SU:116-117, 127
                 dpm_state.update(pred_original)
                 dpm_state.update_lower_order()
@@ -458,12 +471,12 @@ def run_sample_step(
             k, _ = _coefs.dance(sigma_schedule, i, args.eta, mode, bf16_v)
             if determistic[i]:
                 _, pred_original, lp, _ = _ops.fused_step(_ops.DANCE, pred, x, k, src=SRC_DETERMINISTIC, sde_solver=False,
-                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd)
+                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
             else:
                 if nz is None:
                     nz = torch.randn(pred.shape, device=dev, dtype=torch.float32)
                 _, pred_original, lp, _ = _ops.fused_step(_ops.DANCE, pred, x, k, src=SRC_NOISE, noise=nz, sde_solver=True,
-                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd)
+                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
         cur = out
         steps_done += 1
 

@@ -75,11 +75,14 @@ def grpo_one_step(args, latents, pre_latents, encoder_hidden_states, pooled_prom
 def sample_reference_model(args, device, transformer, encoder_hidden_states, pooled_prompt_embeds, text_ids,
                            decode_and_score: Callable[[torch.Tensor], object], timesteps_train: Sequence[int], *,
                            input_latents: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None,
-                           noises=None):
+                           noises=None, vae_input: bool = False):
     """TR:184-329 for a whole batch of ``B = encoder_hidden_states.shape[0]`` samples at once.
 
     ``decode_and_score(latents (B, S, 64) fp32) -> rewards`` stands for unpack + VAE decode + reward models
     (TR:284-316; out of scope) and returns a tensor ``[B]`` (reward_aggr) or a dict of tensors (advantage_aggr).
+    ``vae_input=True``: the callback receives what TR:286-287 hands to ``vae.decode`` instead — ``unpack_latents(latents, h, w,
+    8) / 0.3611 + 0.1159`` as fp32 ``(B, 16, h/8, w/8)`` — written by the LAST sampler step as a second output (no unpack
+    launch, no extra pass over the final latent; bit-identical to the two torch ops on CUDA).
     Returns ``(rewards, all_latents, all_log_probs, sigma_schedule, image_ids)`` like TR:329."""
     w, h = args.w, args.h
     sigma_schedule = torch.linspace(1, 0, args.sampling_steps + 1).to(device)
@@ -97,11 +100,12 @@ def sample_reference_model(args, device, transformer, encoder_hidden_states, poo
         determistic = _rollout.window_mask(args.sampling_steps, timesteps_train, "part")
     else:
         determistic = [False] * args.sampling_steps
+    dec = {"height": h, "width": w, "vae_scale_factor": 8, "divisor": 0.3611, "shift": 0.1159, "reciprocal": True} if vae_input else None
     with torch.no_grad():
         _, latents, all_latents, all_log_probs = run_sample_step(
             args, z, range(args.sampling_steps), sigma_schedule, transformer, encoder_hidden_states, pooled_prompt_embeds,
-            text_ids[:1], image_ids, True, determistic, noises=noises)
-        rewards = decode_and_score(latents)
+            text_ids[:1], image_ids, True, determistic, noises=noises, decode=dec)
+        rewards = decode_and_score(dec["out"] if vae_input else latents)
     return rewards, all_latents, all_log_probs, sigma_schedule, image_ids
 
 
@@ -175,7 +179,7 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
                    reward_weights, encoder_hidden_states, pooled_prompt_embeds, text_ids, *, exchange=None,
                    on_accumulated: Optional[Callable[[int], None]] = None, micro_batch: int = 1,
                    input_latents: Optional[torch.Tensor] = None, noises=None, generator: Optional[torch.Generator] = None,
-                   rng=None, split_groups: bool = False):
+                   rng=None, split_groups: bool = False, vae_input: bool = False):
     """The hot path of the reference's ``train_one_step`` (TR:341-640) as one call: prompt repetition (TR:369-384), batched
     rollout (TR:386-399), sample bookkeeping (TR:400-415), reward exchange + group-relative advantages (TR:417-501), step
     permutation / positive-negative re-ranging (TR:503-535), the (sample, window step) policy-update loop (TR:536-615) and
@@ -188,6 +192,8 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
     ``split_groups`` (SURVEY §8e extended mode): a prompt group is spread over several ranks — ``num_generations`` counts the
     samples of a group across ranks, consecutive in rank-major order, and the statistics come from the gathered rewards;
     each rank repeats its prompt ``num_generations // world`` times.
+    ``vae_input``: ``decode_and_score`` receives the VAE-ready tensor written by the last sampler step (see
+    ``sample_reference_model``).
     Returns ``(stats [4] = total_loss, policy_total_loss, kl_total_loss, total_clip_frac — rank-averaged device tensor,
     gathered_reward_res (per-model mean of the gathered rewards, device tensors), samples, advantages)``; nothing syncs the
     host except the optional ``advantage_rerange_strategy`` (which needs the advantages' signs, like the reference)."""
@@ -201,7 +207,7 @@ def train_one_step(args, device, transformer, decode_and_score: Callable[[torch.
         encoder_hidden_states, pooled_prompt_embeds, text_ids = rep(encoder_hidden_states), rep(pooled_prompt_embeds), rep(text_ids)
     rewards, all_latents, all_log_probs, sigma_schedule, image_ids = sample_reference_model(
         args, device, transformer, encoder_hidden_states, pooled_prompt_embeds, text_ids, decode_and_score, timesteps_train,
-        input_latents=input_latents, generator=generator, noises=noises)
+        input_latents=input_latents, generator=generator, noises=noises, vae_input=vae_input)
     samples = _rollout.make_samples(all_latents, all_log_probs, sigma_schedule, args.sampling_steps)        # TR:400-415
     rewards = {k: v.to(torch.float32) for k, v in rewards.items()} if isinstance(rewards, dict) else rewards.to(torch.float32)
     use_group = getattr(args, "use_group", True)

@@ -232,3 +232,35 @@ def test_config0_train_one_step_composition():
             assert torch.allclose(gres, merged.mean())
     finally:
         px.close()
+
+
+@pytest.mark.parametrize("drop_last", [False, True])
+def test_sample_reference_model_hands_the_vae_its_input(drop_last):
+    """TR:284-287 inside the rollout: with ``vae_input=True`` the decode/score callback receives
+    ``unpack_latents(latents, h, w, 8) / 0.3611 + 0.1159`` written by the LAST sampler step — bit-identical to the two torch
+    ops the reference runs on the device after the loop, the trajectory untouched, one launch fewer."""
+    from mixgrpo_b200 import ops, trainer
+    args = _args(drop_last_sample=drop_last)
+    model, enc, pooled, text_ids, lat0, noises, rewards = _setup(5)
+    model.eval()
+    seen = {}
+
+    def score_plain(lat):
+        seen["plain"] = lat
+        return rewards
+
+    def score_vae(x):
+        seen["vae"] = x
+        return rewards
+
+    before = ops.launch_count
+    _, lat_a, lp_a, _, _ = trainer.sample_reference_model(args, DEV, model, enc, pooled, text_ids, score_plain, WINDOW, input_latents=lat0, noises=noises)
+    n_plain = ops.launch_count - before
+    before = ops.launch_count
+    _, lat_b, lp_b, _, _ = trainer.sample_reference_model(args, DEV, model, enc, pooled, text_ids, score_vae, WINDOW, input_latents=lat0, noises=noises,
+                                                          vae_input=True)
+    assert ops.launch_count - before == n_plain, "the VAE input costs no extra launch"
+    assert torch.equal(lat_a, lat_b) and torch.equal(lp_a, lp_b)
+    want = GO.unpack(seen["plain"].float(), args.h, args.w, 8) / 0.3611 + 0.1159           # TR:286-287, evaluated on the device like the reference
+    assert seen["vae"].shape == (G, 16, 32, 32) and seen["vae"].dtype == torch.float32
+    assert torch.equal(seen["vae"], want)
