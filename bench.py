@@ -58,6 +58,7 @@ SCENARIOS = {
     "large_b24_1024sq": (24, 4096, torch.bfloat16, False),      # configs[4]
     "large_b24_512sq_bf16": (24, 1024, torch.bfloat16, False),  # configs[4]
     "large_b24_512sq_f32": (24, 1024, torch.float32, False),    # configs[4], fp32 model output and noise
+    "mixgrpo_ode_logp_off": (12, 4096, torch.bfloat16, False),  # configs[1] with SamplerConfig.ode_log_probs=False (dead columns skipped)
 }
 WORKLOAD_TEXT = {
     "mixgrpo": "FLUX.1-dev-shape 1024^2 packed latents (12,4096,64), group 12, 25 steps, SDE window 4 (BASELINE configs[1]); one prompt group per GPU",
@@ -65,6 +66,7 @@ WORKLOAD_TEXT = {
     "large_b24_1024sq": "BASELINE configs[4]: group 24 at 1024^2 (24,4096,64), bf16 model output, 25 steps, SDE window 4",
     "large_b24_512sq_bf16": "BASELINE configs[4]: group 24 at 512^2 (24,1024,64), bf16 model output, 25 steps, SDE window 4",
     "large_b24_512sq_f32": "BASELINE configs[4]: group 24 at 512^2 (24,1024,64), fp32 model output and noise, 25 steps, SDE window 4",
+    "mixgrpo_ode_logp_off": "configs[1] with SamplerConfig.ode_log_probs=False: the 21 deterministic steps skip the log-prob reduction (columns the reference computes but train_one_step never reads, TR:536-553); same bytes, trajectory and window log-probs bit-identical",
 }
 
 
@@ -192,6 +194,8 @@ class Workload:
         self.window = list(range(WINDOW))
         self.plan, self.n_steps = step_plan(self.flash, self.window)
         self.cfg = sampler_config(self.flash)
+        if name == "mixgrpo_ode_logp_off":
+            self.cfg.ode_log_probs = False
         self.sig = R.sigma_schedule(N_STEPS, SHIFT)                        # host schedule: no per-step sync
         self.z0 = torch.randn(B, S, C, device=dev, generator=g).bfloat16()
         if v32 is not None:                                                # same underlying values in another dtype (fp32-vs-bf16 check)
@@ -362,6 +366,7 @@ def measure_kernels(dev, peak_gbs, B=12, S=4096, full=True):
 
     common = dict(round_like_torch=True, early=1)
     rec("ode", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], out_logp=lps[i], want_x0=False, **common)), ns, s), "ode")
+    rec("ode_no_logp", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_logp=False, want_x0=False, **common)), ns, s), "ode")
     rec("sde", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=False, **common)), ns, s), "sde")
     rec("sde_x0", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], **common)), ns, s), "sde_x0")
     if not full:
@@ -797,7 +802,7 @@ def run_native(args):
         del graphs, graph
         torch.cuda.empty_cache()
         configs, ksteps = {}, max(5, min(args.steps, 50))
-        for nm in ("flash", "large_b24_1024sq"):
+        for nm in ("flash", "large_b24_1024sq", "mixgrpo_ode_logp_off"):
             configs[nm], _ = time_scenario(nm, dev, rank, world, ksteps, w.px)
             torch.cuda.empty_cache()
         # fp32 vs bf16 at (24,1024,64): the SAME model outputs / noise, once in fp32 and once rounded to bf16
@@ -1015,7 +1020,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--config", default="mixgrpo", choices=["mixgrpo", "flash", "large", "large_b24_1024sq", "large_b24_512sq_bf16", "large_b24_512sq_f32"],
+    ap.add_argument("--config", default="mixgrpo", choices=["mixgrpo", "flash", "large", "large_b24_1024sq", "large_b24_512sq_bf16", "large_b24_512sq_f32", "mixgrpo_ode_logp_off"],
                     help="which BASELINE config is the line's headline workload (default configs[1]; the default line also carries the others under `configs`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[3] / configs[4] lines")

@@ -48,6 +48,11 @@ class SamplerConfig:
     # immediately before it on the stream (true when `model` returns precomputed tensors or when its last kernel is not the
     # producer of v; after a real DiT forward the attribute is inert anyway) -> v / noise loads overlap the previous step's drain
     pdl_early_v: bool = False
+    # all_log_probs[:, i] of a DETERMINISTIC step is dead data in the reference itself: train_one_step only ever indexes the
+    # SDE-window steps (TR:536-553), and with training_strategy "all" every step is an SDE step.  True (default) computes it
+    # anyway, exactly like the reference (SU:201-208 runs on every step); False skips the reduction on ODE steps (their CTAs
+    # retire right after their stores: -0.5 us per launch at (12,4096,64)) and leaves NaN in those columns.
+    ode_log_probs: bool = True
 
 
 def sigma_schedule(sampling_steps: int, shift: float, device=None) -> torch.Tensor:
@@ -96,7 +101,10 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
     B, dev = z.shape[0], z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
     _ops.cast_rows(z, traj[:, 0])
-    logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
+    if cfg.ode_log_probs:
+        logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
+    else:
+        logps_t = torch.full((n_steps, B), float("nan"), dtype=torch.float32, device=dev)       # skipped columns stay poisoned
     host_sig = _coefs.host_schedule(sigmas).tolist()
     x0 = None
     need_x0_last = cfg.drop_last_sample or want_x0
@@ -127,9 +135,11 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
             k, _ = _coefs.dpm(sigmas, i, order, cfg.dpm_algorithm_type, cfg.dpm_solver_type, mode, bf16_v)
             if sde and nz is None:
                 nz = torch.randn(v.shape, device=dev, dtype=torch.float32)
+            lp_on = sde or cfg.ode_log_probs
             _, x0, _, _ = _ops.fused_step(_ops.DPM, v, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
                                           noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
-                                          out_logp=logps_t[i], want_x0=True, round_like_torch=rnd, early=early, decode=dec)
+                                          out_logp=logps_t[i] if lp_on else None, want_logp=lp_on, want_x0=True, round_like_torch=rnd,
+                                          early=early, decode=dec)
             dpm_state.update(x0)
             dpm_state.update_lower_order()
         else:
@@ -145,8 +155,10 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
                 src = SRC_NOISE
                 if nz is None:
                     nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32, generator=generator)
+            lp_on = (not determistic[i]) or cfg.ode_log_probs
             _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
-                                          out_logp=logps_t[i], want_x0=keep_x0, round_like_torch=rnd, early=early, decode=dec)
+                                          out_logp=logps_t[i] if lp_on else None, want_logp=lp_on, want_x0=keep_x0, round_like_torch=rnd,
+                                          early=early, decode=dec)
             if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
                 dpm_state.update(x0)
                 dpm_state.update_lower_order()

@@ -285,3 +285,27 @@ def test_dpm_first_order_logprob_backward_vs_oracle_autograd(algo, dtype):
         su.flow_grpo_step(vd, x.to(d), ETA, SIG, idx, None, determistic=True)
     with torch.no_grad():
         su.flow_grpo_step(vd, x.to(d), ETA, SIG, idx, None, determistic=True)          # fine without grad mode
+
+
+# ------------------------------------------------------------------------------------------ ODE-step log-probs are optional
+@pytest.mark.parametrize("flash", [False, True])
+def test_rollout_without_ode_log_probs_changes_nothing_that_is_read(flash):
+    """SamplerConfig.ode_log_probs=False: deterministic steps skip the reduction.  The trajectory and the SDE-window log-probs
+    (all train_one_step ever reads, TR:536-553) are bit-identical; the skipped columns are NaN, not stale memory."""
+    from mixgrpo_b200 import rollout as R
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(9)
+    B, S, N = 4, 256, 25
+    window = [2, 3, 4, 5]
+    kw = dict(dpm_algorithm_type="dpmsolver++", dpm_apply_strategy="post") if flash else {}
+    z0 = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    vs = [torch.randn(B, S, 64, device=d, generator=g).bfloat16() for _ in range(N)]
+    nz = [torch.randn(B, S, 64, device=d, generator=g).bfloat16() if i in window else None for i in range(N)]
+    det = R.window_mask(N, window)
+    sig = R.sigma_schedule(N, 3.0)
+    a = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(**kw), noises=nz)
+    b = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(ode_log_probs=False, **kw), noises=nz)
+    assert torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[3][:, window], b[3][:, window])
+    ode = [i for i in range(a[3].shape[1]) if i not in window]
+    assert torch.isnan(b[3][:, ode]).all() and torch.isfinite(a[3][:, [i for i in ode if i < a[3].shape[1] - 1]]).all()
