@@ -106,11 +106,10 @@ typedef struct mixgrpo_step_coefs {
   float c[16];
 } mixgrpo_step_coefs;
 
-/* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 64-byte record per
- * sample — a 64-bit packed accumulator ([fixed-point sum | wide-share count | arrival count], csrc/step_kernel.cuh) for
- * the deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu), two 64-bit side
- * accumulators for shares too large for the packed field, and the start-ticket counter of the deferred finalization
- * (csrc/step_math.cuh).  The layout does
+/* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 32-byte record per
+ * sample — a 64-bit packed accumulator ([fixed-point sum | wide-share count | arrival count], csrc/step_kernels.cu) for
+ * the deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu), and a 64-bit side
+ * accumulator for shares too large for the packed field (csrc/step_math.cuh).  The layout does
  * not depend on B and kernels leave the accumulators zeroed again, so one allocation can be reused by successive
  * launches of any batch size on the same stream (never by launches that may run concurrently). */
 int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);

@@ -40,9 +40,6 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   const float* xp = q.x + (long long)b * q.x_bs;
   const float* ap = q.x_in + (long long)b * q.in_bs;
   float acc = 0.f;
-  unsigned ticket = 0;                               // deferred finalization (step_math.cuh): start ticket, consumed at the end
-  unsigned long long* rec = p.acc + kWsStride * (long long)blockIdx.y;
-  if (p.early == 0 && threadIdx.x == 0) ticket = take_ticket(rec);
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * kTile + threadIdx.x * kVec;
     if (off >= n) continue;
@@ -50,7 +47,7 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
     ld_stream(vp + off, v);
     ld_stream(xp + off, x);
     ld_stream(ap + off, a);
-    if (p.early != 0) { pdl_prologue(); if (threadIdx.x == 0) ticket = take_ticket(rec); }   // grid.x == tiles: the first iteration is the only one
+    if (p.early != 0) pdl_prologue();               // grid.x == tiles: the first iteration is the only one
 #pragma unroll
     for (int j = 0; j < kVec; j += 2) {
       const float v2[2] = {v[j], v[j + 1]}, x2[2] = {x[j], x[j + 1]}, a2[2] = {a[j], a[j + 1]}, z2[2] = {0.f, 0.f};
@@ -71,10 +68,14 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   if (lane == 0) {
     const int ctas = gridDim.x;
     const float r = __fdiv_rn(t, __fmul_rn((float)n, q.k.two_var));
-    float s;
-    if (packed_arrive(r, ctas, ticket, rec, &s)) {
+    unsigned long long* rec = p.acc + kWsStride * (long long)blockIdx.y;
+    const unsigned long long add = packed_share(r, ctas, rec);
+    const unsigned long long old = atomicAdd(rec, add);
+    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
+      const float s = packed_total(old + add, rec);
       const float lp = __fsub_rn(__fsub_rn(-s, q.k.log_scale), q.k.log_norm);        // SU:201-208
       q.logp[b] = lp;
+      *rec = 0ull;
       if (q.rows) {                                                                    // TR:560-583, the reference's B == 1 evaluation
         const LossTerms lt = loss_terms(lp, q.old_lp[b], p.loss.adv[b], p.loss, 1.f);
         const float policy = __fdiv_rn(lt.policy_num, p.loss.denom);

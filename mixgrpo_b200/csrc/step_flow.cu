@@ -11,10 +11,9 @@ using namespace mg;
 
 extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n) {
   if (B <= 0 || n <= 0) return 0;
-  // one 64-byte record per sample: { packed 64-bit accumulator | 32-bit epoch | 32-bit status (record 0) | 64-bit side
-  // accumulator (Q39.24) for oversized shares | 64-bit integer accumulator for shares above 2^27 | 64-bit start-ticket
-  // counter | pad } — the layout does not depend on B, so calls with different batch sizes can share one zero-initialised
-  // allocation
+  // one 32-byte record per sample: { packed 64-bit accumulator | 32-bit epoch | 32-bit status (record 0) | 64-bit side
+  // accumulator (Q39.24) for oversized shares | 64-bit integer accumulator for shares above 2^27 } — the layout does not depend on B, so calls with different batch sizes can
+  // share one zero-initialised allocation
   return ((B * (int64_t)(kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
 }
 

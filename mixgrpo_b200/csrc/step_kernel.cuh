@@ -74,12 +74,12 @@ __device__ __forceinline__ void store_decoded(const StepParams& p, int b, long l
 // without waiting on anything (a persistent / software-pipelined variant and every fence+ticket
 // reduction were 20-30 % slower).
 //
-// log-prob reduction — one fire-and-forget atomic per CTA, deterministic, no fence:
-//   acc[b] is a 64-bit word  [ sum : 40 bit fixed point Q8.32 | wide-share count : 12 | arrivals : 12 ].
-//   A CTA adds  (1, wide?, round(r * 2^32))  with r = sum_cta(d^2) / (n * 2 s^2)  in ONE RED (no return value).
-//   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in.  The CTA that STARTED
-//   last (a ticket taken at CTA start, its latency hidden behind the loads) waits until the word shows all arrivals,
-//   writes logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the record for the next launch (step_math.cuh).
+// log-prob reduction — one atomic per CTA, deterministic, no fence:
+//   acc[b] is a 64-bit word  [ sum : 40 bit fixed point Q8.32 | poison : 12 | arrivals : 12 ].
+//   A CTA adds  (1, poison?, round(r * 2^32))  with r = sum_cta(d^2) / (n * 2 s^2)  in ONE atomicAdd.
+//   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in; the CTA
+//   whose returned count is the last one owns the complete sum in (old + mine), writes
+//   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
 //   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2).  A share too large for the field (> 255/ctas)
 //   goes into the record's 64-bit side accumulators instead (packed_share / packed_total in step_math.cuh), so the
 //   log-prob stays finite like the reference's up to |d|/s ~ 4e7; only a non-finite share (or one beyond that) gives NaN.
@@ -127,11 +127,6 @@ step_kernel(const __grid_constant__ StepParams p) {
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
   const float* xp = p.x + (long long)b * p.x_bs;
   float acc = 0.f;
-  // start ticket of the deferred log-prob finalization (step_math.cuh): taken after the dependency wait — the previous
-  // launch's finalizer re-zeroes the record — and consumed only at the end, so its round trip hides behind the loads
-  unsigned ticket = 0;
-  const bool reducer = p.logp_out != nullptr && threadIdx.x == 0;
-  if (p.early == 0 && reducer) ticket = take_ticket(p.acc + kWsStride * b);
 
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * kTile;
@@ -140,7 +135,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     float v[kVec], x[kVec], a[kVec], m1[kVec], m2[kVec];
     load_tile<VT, VECTOR>(vp, off, n, v);
     if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
-    if (p.early == 1) { pdl_prologue(); if (reducer) ticket = take_ticket(p.acc + kWsStride * b); }
+    if (p.early == 1) pdl_prologue();
     load_tile<float, VECTOR>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_PHILOX) {     // draw the noise here: element e -> component e%4 of Philox(e/4)
       unsigned long long ph_seed = p.philox_seed, ph_off = p.philox_offset;
@@ -166,7 +161,7 @@ step_kernel(const __grid_constant__ StepParams p) {
     if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR>(p.x_in + (long long)b * p.in_bs, off, n, a);
     if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
     if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
-    if (p.early == 2) { pdl_prologue(); if (reducer) ticket = take_ticket(p.acc + kWsStride * b); }
+    if (p.early == 2) pdl_prologue();
 
     float xn[kVec], x0[OUT >= 1 ? kVec : 2], mu[OUT == 2 ? kVec : 2];
 #pragma unroll
@@ -209,11 +204,14 @@ step_kernel(const __grid_constant__ StepParams p) {
     const int ctas = gridDim.x;
     const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
     unsigned long long* rec = p.acc + kWsStride * b;
-    float q;
-    if (packed_arrive(r, ctas, ticket, rec, &q)) {
+    const unsigned long long add = packed_share(r, ctas, rec);
+    const unsigned long long old = atomicAdd(rec, add);
+    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
+      const float q = packed_total(old + add, rec);
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
       p.logp_out[b] = lp;
+      p.acc[kWsStride * b] = 0ull;
       if constexpr (SRC == MIXGRPO_SRC_GIVEN) {
         // fused policy path: the sample's clipped-ratio loss terms (TR:560-583, one sample = the reference's B == 1)
         // are added to its own stats row by this single thread — ordered across launches, no extra kernel

@@ -14,10 +14,9 @@ enum Family { kFlow = 0, kDance = 1, kDpm = 2 };
 constexpr int kTile = kThreads * kVec;          // scalars per CTA-tile
 constexpr int kCountBits = 12, kPoisonBits = 12;
 constexpr int kMaxCtasPerSample = (1 << kCountBits) - 1;
-// workspace record per sample (in 64-bit words): { accumulator, { epoch : 32 | status : 32 }, wide side accumulator, integer side
-// accumulator, start ticket, 3 x pad } = 64 bytes — see mixgrpo_step_workspace_bytes
-constexpr int kWsStride = 8;
-constexpr int kWsTicket = 4;                    // word index of the start-ticket counter inside a record
+// workspace record per sample (in 64-bit words): { accumulator, { epoch : 32 | status : 32 }, wide side accumulator, pad }
+// — see mixgrpo_step_workspace_bytes
+constexpr int kWsStride = 4;
 constexpr int kWsWide = 2;                      // word index of the side accumulator inside a record
 constexpr int kWsHuge = 3;                      // word index of the second side accumulator (integer units)
 constexpr float kWideCap = 134217728.f;         // 2^27: largest per-CTA share the Q39.24 side accumulator takes (4095 CTAs x 2^27 x 2^24 < 2^63)
@@ -57,56 +56,6 @@ __device__ __forceinline__ float packed_total(unsigned long long tot, unsigned l
     q += (double)wide * (1.0 / 16777216.0) + (double)huge;
   }
   return (float)q;
-}
-
-// ------------------------------------------------------------------ deferred finalization (step / window-forward kernels)
-// A returning atomic at the END of a CTA keeps the CTA's registers and its slot on the SM allocated for a whole L2 round
-// trip after its last store has been issued — measured: 1.1 us of a 6.8 us Euler-ODE launch at (12,4096,64), the difference
-// between 0.71 and 0.84 of the HBM roofline (bench.py `kernels.ode` vs `ode_no_logp`).  So the round trip moves to the START
-// of the CTA, where it hides behind the tile's load latency:
-//   start  one thread takes a ticket (returning atomicAdd on the record's ticket word; the value is not needed until the end)
-//   end    the same thread adds the CTA's packed share with a fire-and-forget RED and the CTA retires —
-//          except the CTA that STARTED last (ticket == ctas - 1): every other CTA of the sample is already running, so it can
-//          wait for them without any assumption on dispatch order; it polls the packed word until all `ctas` arrivals are in,
-//          folds the side words in, writes the log-prob and re-zeroes the record (graph-replay safe).
-// The packed word, the shares and therefore every bit of the result are unchanged (integer adds commute).  The wait is bounded
-// (kFinalizeSpinNs): a record that never completes — a caller sharing one workspace between concurrent launches — yields NaN.
-constexpr unsigned long long kFinalizeSpinNs = 2000000000ull;
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ unsigned take_ticket(unsigned long long* rec) {
-  return (unsigned)atomicAdd(rec + kWsTicket, 1ull);
-}
-
-// returns true on the ONE thread per sample that owns the complete sum; *q = mean(d^2 / 2 s^2)
-__device__ __forceinline__ bool packed_arrive(float r, int ctas, unsigned ticket, unsigned long long* rec, float* q) {
-  atomicAdd(rec, packed_share(r, ctas, rec));          // result unused: compiles to RED.E.ADD.64 (no round trip)
-  if (ticket != (unsigned)(ctas - 1)) return false;
-  unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(rec);
-  if ((w & (unsigned long long)kMaxCtasPerSample) != (unsigned long long)ctas) {
-    const unsigned long long t0 = globaltimer_ns();
-    unsigned spins = 0;
-    for (;;) {
-      __nanosleep(40);
-      w = *reinterpret_cast<volatile unsigned long long*>(rec);
-      if ((w & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)ctas) break;
-      if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > kFinalizeSpinNs) {
-        *q = __int_as_float(0x7fc00000);
-        atomicExch(rec + kWsWide, 0ull); atomicExch(rec + kWsHuge, 0ull);
-        rec[0] = 0ull; rec[kWsTicket] = 0ull;
-        return true;
-      }
-    }
-  }
-  *q = packed_total(w, rec);
-  rec[0] = 0ull;
-  rec[kWsTicket] = 0ull;
-  return true;
 }
 
 // ------------------------------------------------------------------ per-tile arithmetic

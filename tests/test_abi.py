@@ -54,9 +54,9 @@ def test_host_side_argument_validation_needs_no_gpu():
     from mixgrpo_b200 import _cabi
     lib = _cabi.lib()
     k = _cabi.StepCoefs()
-    assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 768        # one 64-byte record per sample, rounded to 256
+    assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 512
     assert lib.mixgrpo_step_workspace_bytes(0, 10) == 0
-    assert lib.mixgrpo_step_workspace_bytes(100, 10) == 6400
+    assert lib.mixgrpo_step_workspace_bytes(100, 10) == 3328
     # null pointers / bad sizes / bad enums are rejected with MIXGRPO_EINVAL before any launch
     assert lib.mixgrpo_flow_step(None, 1, None, 0, None, None, 0, None, 0, None, None, None, None, 0, 1, 8, ctypes.byref(k), 0, 0, None, None) == -1
     assert lib.mixgrpo_dpm_step(1, 1, 1, 8, None, None, None, 4, None, 8, None, None, None, None, 0, 1, 8, ctypes.byref(k), 2, 0, None, None) == -1
