@@ -365,10 +365,18 @@ def measure_kernels(dev, peak_gbs, B=12, S=4096, full=True):
         return lambda: [fn(i) for i in range(ns)]
 
     common = dict(round_like_torch=True, early=1)
-    rec("ode", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], out_logp=lps[i], want_x0=False, **common)), ns, s), "ode")
-    rec("ode_no_logp", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_logp=False, want_x0=False, **common)), ns, s), "ode")
-    rec("sde", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=False, **common)), ns, s), "sde")
-    rec("sde_x0", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], **common)), ns, s), "sde_x0")
+    # as the rollout launches them: the step only accumulates its log-prob sums (MIXGRPO_FLAG_DEFER_LOGP) and ONE finalize launch
+    # per rollout writes every step's log-probs — here one finalize per 10 step launches, inside the timed graph
+    acc = ops.DeferredLogProbs(dev, ns, B, S * C)
+    def deferred(fn):
+        def run():
+            for i in range(ns):
+                fn(i)
+            acc.finalize(lps)
+        return run
+    rec("ode", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_x0=False, defer=acc.slot(i, k), **common)), ns, s), "ode")
+    rec("sde", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=False, defer=acc.slot(i, k), **common)), ns, s), "sde")
+    rec("sde_x0", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=True, out_x0=x0s[i], defer=acc.slot(i, k), **common)), ns, s), "sde_x0")
     if not full:
         return res
     # the window's policy update as the step launches it: 4 forwards in ONE launch, 4 backwards in ONE launch
@@ -386,6 +394,10 @@ def measure_kernels(dev, peak_gbs, B=12, S=4096, full=True):
                                   out_grads=[gvs[i] for i in idx])
     rec("train_fwd_x4 (one launch)", _time_graph(lambda: [fwd_multi(q) for q in range(nq)], nq, s), "train_fwd", J)
     rec("bwd_x4 (one launch)", _time_graph(lambda: [bwd_multi(q) for q in range(nq)], nq, s), "bwd", J)
+    # the drop-in operators return their log-prob at once: same kernels with the returning atomic (flow_grpo_step & co.)
+    rec("ode_immediate", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], out_logp=lps[i], want_x0=False, **common)), ns, s), "ode")
+    rec("ode_no_logp", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_logp=False, want_x0=False, **common)), ns, s), "ode")
+    rec("sde_x0_immediate", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], **common)), ns, s), "sde_x0")
     rec("train_fwd", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_GIVEN, x_next=outs[(i + 1) % ns], out_logp=lps[i], want_x0=False, round_like_torch=True)), ns, s), "train_fwd")
     rec("bwd", _time_graph(loop(lambda i: ops.logprob_backward(ops.FLOW, vs[i], xs[i], outs[(i + 1) % ns], glp, k, True, out=gvs[i])), ns, s), "bwd")
     rec("sde_x0_philox", _time_graph(loop(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_PHILOX, philox=(1234, 4 * i), out_x_next=outs[i], out_logp=lps[i], want_x0=True, out_x0=x0s[i], round_like_torch=True)), ns, s), "sde_x0_philox")
@@ -416,7 +428,7 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     tot_b = sum(res[k]["bytes_per_elem"] * e * c for k, c, _ in plan)
     tot_us = sum(res[k]["us_per_launch"] * c for k, c, _ in plan)
     roof = {"bound": "hbm",
-            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 29 launches and the largest share of its device time",
+            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 30 launches and the largest share of its device time; launched as the rollout launches it (log-prob sums accumulated, one finalize launch per rollout — included in the time, one per 10 launches here)",
             "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
             "unit": "GB/s", "frac": round(top["GBps"] / peak_gbs, 4), "traffic": None, "us_per_launch": top["us_per_launch"],
             "algorithmic_bytes_per_launch": e * bytes_per_elem("ode", False),

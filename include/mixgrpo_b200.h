@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MIXGRPO_ABI_VERSION 4
+#define MIXGRPO_ABI_VERSION 5
 
 /* element type of model_output / noise / grad_model_output */
 enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
@@ -66,6 +66,14 @@ typedef struct mixgrpo_philox_args {
                                             preceding launch (they come from the DiT / randn, several launches back) but
                                             the latents may have been (step i reads what step i-1 wrote): only v / noise
                                             are loaded before the wait */
+
+#define MIXGRPO_FLAG_DEFER_LOGP       8u /* step kernels: accumulate the launch's per-sample log-prob sums into `workspace` — then the
+                                            CALLER's own B records for THIS launch, mixgrpo_step_workspace_bytes(B, n) bytes, zeroed —
+                                            with a fire-and-forget reduction and do not finalize; logp_out may be NULL.  A rollout's
+                                            log-probs are only read after the rollout (SU:153-155), so its 25 step launches skip the
+                                            returning atomic that otherwise keeps every CTA resident for an L2 round trip (0.7 us of a
+                                            7 us launch at (12,4096,64)); ONE mixgrpo_logp_finalize launch then turns all records into
+                                            log-probs.  Same packed integer sums, hence the same bits as the immediate path. */
 
 /* error codes */
 #define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
@@ -176,6 +184,16 @@ int mixgrpo_dpm_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
                      float* logp_out, void* workspace, int64_t workspace_bytes,
                      int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
                      int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext);
+
+/* Finalizes the log-probs of `n_launches` step launches issued with MIXGRPO_FLAG_DEFER_LOGP (stream-ordered after them; ONE
+ * launch): launch i accumulated into the B records at workspace + i * launch_stride_bytes;
+ *   logp_out[i * out_stride + b] = -mean(d^2 / 2 s^2) - log_scale_host[i] - log_norm_host[i]      (SU:201-208)
+ * with the per-step scalars of that launch's mixgrpo_step_coefs.  active_host[i] == 0 (nullable = all active): launch i did not
+ * accumulate (e.g. a deterministic step whose log-prob was skipped) — its row is filled with NaN.  Records are left zeroed.
+ * n_launches <= 4096 (chunks of 64 per kernel launch). */
+int mixgrpo_logp_finalize(void* workspace, int64_t launch_stride_bytes, int64_t n_launches, int64_t B,
+                          const float* log_scale_host, const float* log_norm_host, const int* active_host,
+                          float* logp_out, int64_t out_stride, void* stream);
 
 /* Moves a graph-safe Philox state's base offset: device_state[1] += increment (one tiny launch, stream-ordered after the
  * step launches that consumed the numbers; issue it once per rollout, captured in the same graph). */

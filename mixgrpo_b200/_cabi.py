@@ -16,11 +16,12 @@ SRC_NOISE, SRC_GIVEN, SRC_DETERMINISTIC, SRC_PHILOX = 0, 1, 2, 3
 FLAG_ROUND_LIKE_TORCH = 1
 FLAG_PDL_EARLY_LOADS = 2
 FLAG_PDL_EARLY_V = 4
+FLAG_DEFER_LOGP = 8
 POLICY_MAX_ITEMS = 8
 ADV_GROUP_LOCAL, ADV_GROUP_SPLIT, ADV_GLOBAL = 0, 1, 2
 EUNSUPPORTED = -4
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class StepCoefs(C.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "mixgrpo_flow_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P, _XP]),
     "mixgrpo_dance_step": (_I, [_P, _I, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _I, _U, _P, _XP]),
     "mixgrpo_dpm_step": (_I, [_P, _I, _P, _I64, _P, _P, _P, _I, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _CP, _I, _U, _P, _XP]),
+    "mixgrpo_logp_finalize": (_I, [_P, _I64, _I64, _I64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), _P, _I64, _P]),
     "mixgrpo_philox_advance": (_I, [_P, C.c_uint64, _P]),
     "mixgrpo_logprob_bwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _CP, _U, _P]),
     "mixgrpo_policy_fwd": (_I, [_I, _P, _I, _P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _CP, _LP, _U, _P]),

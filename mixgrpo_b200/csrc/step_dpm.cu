@@ -16,7 +16,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_dpm_step(const voi
                                 int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
                                 int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext) {
   int err = 0;
-  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
+  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err, (flags & MIXGRPO_FLAG_DEFER_LOGP) != 0)) return err ? err : MIXGRPO_EINVAL;
   if (order < 1 || order > 3 || (order >= 2 && !m1) || (order == 3 && !m2)) return MIXGRPO_EINVAL;
   if ((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) return MIXGRPO_EINVAL;
   StepParams p;

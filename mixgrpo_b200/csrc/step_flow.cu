@@ -38,7 +38,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_flow_step(const vo
                                  int64_t workspace_bytes, int64_t B, int64_t n, const mixgrpo_step_coefs* coefs_host,
                                  int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext) {
   int err = 0;
-  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err)) return err ? err : MIXGRPO_EINVAL;
+  if (!coefs_host || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err, (flags & MIXGRPO_FLAG_DEFER_LOGP) != 0)) return err ? err : MIXGRPO_EINVAL;
   if (((src == MIXGRPO_SRC_NOISE || src == MIXGRPO_SRC_PHILOX) && !noise) || (src == MIXGRPO_SRC_GIVEN && !x_next_in)) return MIXGRPO_EINVAL;
   StepParams p;
   fill(p, v, x, x_bs, src == MIXGRPO_SRC_PHILOX ? nullptr : noise, x_next_in, in_bs, nullptr, nullptr, x_next_out, out_bs, x0_out, mean_out, logp_out, workspace, B, n, coefs_host);
@@ -62,6 +62,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int fam
   if (!coefs_host || !logp_out || !x_next || !check_common(v, x, B, n, v_dtype, workspace, workspace_bytes, logp_out, &err))
     return err ? err : MIXGRPO_EINVAL;
   if (family != kFlow && family != kDance) return MIXGRPO_EINVAL;
+  if (flags & MIXGRPO_FLAG_DEFER_LOGP) return MIXGRPO_EINVAL;             // the fused loss needs the log-prob inside this launch
   if (loss && (!loss->old_logp || !loss->advantages)) return MIXGRPO_EINVAL;
   StepParams p;
   fill(p, v, x, x_bs, nullptr, x_next, in_bs, nullptr, nullptr, nullptr, n, nullptr, nullptr, logp_out, workspace, B, n, coefs_host);
@@ -84,11 +85,66 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_fwd(int fam
 }
 
 namespace mg {
+constexpr int kFinalizeChunk = 64;
+struct FinalizeParams {
+  unsigned long long* ws;
+  float* out;
+  long long stride_words, out_stride;
+  int B, n_launches;
+  float log_scale[kFinalizeChunk], log_norm[kFinalizeChunk];
+  unsigned long long active;                      // bit i: launch i accumulated
+};
+
+// one thread per (launch, sample) record: fold the side words in, write the log-prob, leave the record zeroed
+__global__ void __launch_bounds__(128) logp_finalize_kernel(const __grid_constant__ FinalizeParams p) {
+  pdl_prologue();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n_launches * p.B) return;
+  const int i = idx / p.B, b = idx - i * p.B;
+  unsigned long long* rec = p.ws + (long long)i * p.stride_words + kWsStride * b;
+  float lp = __int_as_float(0x7fc00000);
+  if ((p.active >> i) & 1ull) {
+    const float q = packed_total(*rec, rec);
+    lp = __fsub_rn(__fsub_rn(-q, p.log_scale[i]), p.log_norm[i]);                 // SU:201-208
+    *rec = 0ull;
+  }
+  p.out[(long long)i * p.out_stride + b] = lp;
+}
+
 __global__ void philox_advance_kernel(unsigned long long* state, unsigned long long inc) {
   pdl_prologue();
   state[1] += inc;
 }
 }  // namespace mg
+
+extern "C" __attribute__((visibility("default"))) int mixgrpo_logp_finalize(void* workspace, int64_t launch_stride_bytes, int64_t n_launches, int64_t B,
+                                                                            const float* log_scale_host, const float* log_norm_host,
+                                                                            const int* active_host, float* logp_out, int64_t out_stride, void* stream) {
+  if (!workspace || !logp_out || !log_scale_host || !log_norm_host || n_launches <= 0 || n_launches > 4096 || B <= 0 || B > 65535 ||
+      launch_stride_bytes < B * (int64_t)(kWsStride * sizeof(unsigned long long)) || (launch_stride_bytes % 8) != 0 || out_stride < B ||
+      (reinterpret_cast<uintptr_t>(workspace) % 8) != 0)
+    return MIXGRPO_EINVAL;
+  for (int64_t lo = 0; lo < n_launches; lo += kFinalizeChunk) {
+    FinalizeParams p;
+    p.n_launches = (int)((n_launches - lo) < kFinalizeChunk ? (n_launches - lo) : kFinalizeChunk);
+    p.B = (int)B;
+    p.stride_words = launch_stride_bytes / 8;
+    p.ws = reinterpret_cast<unsigned long long*>(workspace) + lo * p.stride_words;
+    p.out = logp_out + lo * out_stride;
+    p.out_stride = out_stride;
+    p.active = 0ull;
+    for (int i = 0; i < p.n_launches; ++i) {
+      p.log_scale[i] = log_scale_host[lo + i];
+      p.log_norm[i] = log_norm_host[lo + i];
+      if (!active_host || active_host[lo + i]) p.active |= 1ull << i;
+    }
+    const int total = p.n_launches * p.B;
+    launch_pdl(logp_finalize_kernel, (total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream), p);
+    const int rc = (int)cudaGetLastError();
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int mixgrpo_philox_advance(uint64_t* device_state, uint64_t increment, void* stream) {
   if (!device_state || (reinterpret_cast<uintptr_t>(device_state) % 8) != 0) return MIXGRPO_EINVAL;

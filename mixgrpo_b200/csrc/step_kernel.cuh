@@ -39,6 +39,7 @@ struct StepParams {
   unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
   const unsigned long long* philox_state;          // SRC_PHILOX, graph-safe: device {seed, base offset} (or nullptr)
   LossParams loss;          // fused policy path (SRC_GIVEN only): old log-probs / advantages / stats rows, or nullptrs
+  int defer;                // MIXGRPO_FLAG_DEFER_LOGP: accumulate only (fire-and-forget), mixgrpo_logp_finalize writes the log-probs
   int early;                // programmatic dependent launch: 0 = wait before any load, 1 = v / noise first, 2 = every input first
   // optional second output: x_next (or x0) unpacked to (B,C,H,W) and de-normalised for the VAE (TR:102-115, TR:286-287)
   float* decode_out;
@@ -190,7 +191,7 @@ step_kernel(const __grid_constant__ StepParams p) {
       else store_decoded(p, b, off + threadIdx.x * kVec, xn);
     }
   }
-  if (p.logp_out == nullptr) return;
+  if (p.logp_out == nullptr && !p.defer) return;
 
   __shared__ float s_warp[kThreads / 32];
   acc = warp_sum(acc);
@@ -205,6 +206,12 @@ step_kernel(const __grid_constant__ StepParams p) {
     const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
     unsigned long long* rec = p.acc + kWsStride * b;
     const unsigned long long add = packed_share(r, ctas, rec);
+    if (p.defer) {
+      // a true reduction (REDG.E.ADD.64): nothing comes back, so the CTA retires without an L2 round trip; the sums are
+      // turned into log-probs by mixgrpo_logp_finalize after the rollout.  Spelled in PTX: nvcc keeps an ATOMG otherwise.
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(rec), "l"(add) : "memory");
+      return;
+    }
     const unsigned long long old = atomicAdd(rec, add);
     if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
       const float q = packed_total(old + add, rec);
@@ -282,14 +289,14 @@ static int pick_src(StepParams& p, int64_t B, int src, bool vec_ok, cudaStream_t
 }
 
 static inline bool check_common(const void* v, const float* x, int64_t B, int64_t n, int v_dtype, void* ws, int64_t ws_bytes,
-                         float* logp, int* err) {
+                         float* logp, int* err, bool defer = false) {
   // grid.y carries the sample index; tile indices are 32-bit inside the kernel
   if (!v || !x || B <= 0 || B > 65535 || n <= 0 || (v_dtype != MIXGRPO_F32 && v_dtype != MIXGRPO_BF16) ||
       (n + kTile - 1) / kTile >= 2147483647LL) {
     *err = MIXGRPO_EINVAL;
     return false;
   }
-  if (logp && (!ws || ws_bytes < mixgrpo_step_workspace_bytes(B, n))) {
+  if ((logp || defer) && (!ws || ws_bytes < mixgrpo_step_workspace_bytes(B, n))) {
     *err = ws ? MIXGRPO_ENOSPACE : MIXGRPO_EINVAL;
     return false;
   }
@@ -307,7 +314,7 @@ static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_
   p.philox_seed = p.philox_offset = 0ull;
   p.philox_state = nullptr;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
-  p.early = 0;
+  p.early = 0; p.defer = 0;
   p.decode_out = nullptr; p.dC = p.dH = p.dW = p.d_from_x0 = p.d_recip = 0; p.d_div = 1.f; p.d_shift = 0.f;
 }
 
@@ -318,6 +325,7 @@ static inline void set_philox(StepParams& p, const void* noise_host) {
 }
 
 static inline void set_early(StepParams& p, unsigned flags) {
+  p.defer = (flags & MIXGRPO_FLAG_DEFER_LOGP) ? 1 : 0;
   p.early = (flags & MIXGRPO_FLAG_PDL_EARLY_LOADS) ? 2 : ((flags & MIXGRPO_FLAG_PDL_EARLY_V) ? 1 : 0);
 }
 

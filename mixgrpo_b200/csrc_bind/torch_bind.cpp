@@ -103,7 +103,7 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
                         const OptT& m1_o, const OptT& m2_o, int order, bool sde_solver, const OptT& out_x_next, bool want_x0, bool want_mean,
                         bool want_logp, bool rnd, const OptT& out_logp, const OptT& out_x0, int early, bool has_philox, uint64_t ph_seed,
                         uint64_t ph_offset, uint64_t ph_state, const OptT& decode_out, double divisor, double shift, bool from_x0,
-                        bool reciprocal) {
+                        bool reciprocal, uint64_t defer_ptr = 0, int64_t defer_bytes = 0) {
   require_cuda(v, "model_output");
   require_cuda(x, "latents");
   x = as_f32(x);
@@ -196,8 +196,9 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
   c10::cuda::OptionalCUDAGuard guard(dev);
   cudaStream_t st = c10::cuda::getCurrentCUDAStream(dev.index()).stream();
   Tensor ws;
-  if (want_logp) ws = workspace(dev, B, n, st);
-  const unsigned flags = make_flags(rnd, vd, early);
+  if (want_logp && !defer_ptr) ws = workspace(dev, B, n, st);
+  // MIXGRPO_FLAG_DEFER_LOGP: accumulate into the caller's records for this launch; mixgrpo_logp_finalize writes the log-probs
+  const unsigned flags = make_flags(rnd, vd, early) | (defer_ptr ? MIXGRPO_FLAG_DEFER_LOGP : 0u);
   mixgrpo_step_ext xe;
   const mixgrpo_step_ext* ext = nullptr;
   if (decode_out) {
@@ -212,8 +213,8 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
   float* x0_p = want_x0 ? o.x0.data_ptr<float>() : nullptr;
   float* mean_p = want_mean ? o.mean.data_ptr<float>() : nullptr;
   float* lp_p = want_logp ? o.logp.data_ptr<float>() : nullptr;
-  void* ws_p = want_logp ? ws.data_ptr() : nullptr;
-  const int64_t ws_n = want_logp ? ws.numel() : 0;
+  void* ws_p = defer_ptr ? reinterpret_cast<void*>(defer_ptr) : (want_logp ? ws.data_ptr() : nullptr);
+  const int64_t ws_n = defer_ptr ? defer_bytes : (want_logp ? ws.numel() : 0);
   int rc;
   if (family == kFlow)
     rc = mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr<float>(), x_bs, noise_p, in_p, in_bs, out_p, out_bs, x0_p, mean_p, lp_p, ws_p, ws_n, B, n, &k,
@@ -338,10 +339,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         [](int family, const Tensor& v, const Tensor& x, uint64_t coefs_addr, int src, const OptT& noise, const OptT& x_next, const OptT& m1, const OptT& m2,
            int order, bool sde_solver, const OptT& out_x_next, bool want_x0, bool want_mean, bool want_logp, bool rnd, const OptT& out_logp,
            const OptT& out_x0, int early, bool has_philox, uint64_t ph_seed, uint64_t ph_offset, uint64_t ph_state, const OptT& decode_out, double divisor,
-           double shift, bool from_x0, bool reciprocal) {
+           double shift, bool from_x0, bool reciprocal, uint64_t defer_ptr, int64_t defer_bytes) {
           StepOut o = fused_step_impl(family, v, x, coefs_at(coefs_addr), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
-                                      want_logp, rnd, out_logp, out_x0, early, has_philox, ph_seed, ph_offset, ph_state, decode_out, divisor, shift,
-                                      from_x0, reciprocal);
+                                      want_logp && !defer_ptr, rnd, out_logp, out_x0, early, has_philox, ph_seed, ph_offset, ph_state, decode_out, divisor,
+                                      shift, from_x0, reciprocal, defer_ptr, defer_bytes);
           return py::make_tuple(opt(o.x_next), opt(o.x0), opt(o.logp), opt(o.mean));
         });
 

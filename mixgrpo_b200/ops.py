@@ -13,7 +13,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (BF16, F32, FLAG_PDL_EARLY_LOADS, FLAG_PDL_EARLY_V, FLAG_ROUND_LIKE_TORCH, POLICY_MAX_ITEMS, SRC_DETERMINISTIC,
+from ._cabi import (BF16, F32, FLAG_DEFER_LOGP, FLAG_PDL_EARLY_LOADS, FLAG_PDL_EARLY_V, FLAG_ROUND_LIKE_TORCH, POLICY_MAX_ITEMS, SRC_DETERMINISTIC,
                     SRC_GIVEN, SRC_NOISE, SRC_PHILOX, LossArgs, PhiloxArgs, PolicyItem, StepCoefs, StepExt)
 
 FLOW, DANCE, DPM = 0, 1, 2
@@ -130,6 +130,54 @@ def _workspace(device: torch.device, B: int, n: int, stream: Optional[int] = Non
     return ws
 
 
+_deferred_bufs: Dict[Tuple[int, int, int], torch.Tensor] = {}
+
+
+class DeferredLogProbs:
+    """Records for ``n_launches`` step launches that only ACCUMULATE their log-prob sums (MIXGRPO_FLAG_DEFER_LOGP) plus the one
+    ``finalize`` launch that turns them into log-probs.  A rollout's log-probs are not read until the rollout is over
+    (SU:153-155), so none of its step launches needs the returning atomic that makes a CTA wait an L2 round trip before it
+    retires; the sums are the same packed integers either way, so the finalized values are bit-identical to the immediate
+    path.  Zeroed once; ``finalize`` leaves the records zeroed (one cached buffer per device, stream and size)."""
+
+    def __init__(self, device: torch.device, n_launches: int, B: int, n: int):
+        self.device, self.n_launches, self.B = device, int(n_launches), int(B)
+        self.stride = int(_cabi.lib().mixgrpo_step_workspace_bytes(B, n))
+        st = _stream_ptr(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), st, self.stride * self.n_launches)
+        buf = _deferred_bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(max(self.stride * self.n_launches, 8), dtype=torch.uint8, device=device)
+            if not torch.cuda.is_current_stream_capturing():
+                if len(_deferred_bufs) > 64:
+                    _deferred_bufs.clear()
+                _deferred_bufs[key] = buf
+        self.buf = buf
+        self.log_scale = (C.c_float * self.n_launches)()
+        self.log_norm = (C.c_float * self.n_launches)()
+        self.active = (C.c_int * self.n_launches)()
+
+    def slot(self, i: int, coefs: StepCoefs) -> Tuple[int, int]:
+        """(device pointer, bytes) of launch ``i``'s records; remembers the step's two log-prob constants for ``finalize``."""
+        self.log_scale[i], self.log_norm[i], self.active[i] = coefs.log_scale, coefs.log_norm, 1
+        return self.buf.data_ptr() + i * self.stride, self.stride
+
+    def finalize(self, out: torch.Tensor) -> torch.Tensor:
+        """out[i, b] (fp32 ``[n_launches, B]``, row stride >= B) = launch i's log-prob of sample b; NaN rows for launches that
+        never took a slot.  One launch."""
+        global launch_count
+        if out.dtype != torch.float32 or out.dim() != 2 or out.shape[0] != self.n_launches or out.shape[1] != self.B or out.stride(1) != 1:
+            raise ValueError("mixgrpo_b200: finalize needs an fp32 [n_launches, B] tensor with contiguous rows")
+        if self.B == 0 or self.n_launches == 0:
+            return out
+        with _on_device(self.device):
+            rc = _cabi.lib().mixgrpo_logp_finalize(self.buf.data_ptr(), self.stride, self.n_launches, self.B, self.log_scale, self.log_norm, self.active,
+                                                   out.data_ptr(), out.stride(0), _stream_ptr(self.device))
+        _cabi.check(rc, "logp_finalize")
+        launch_count += 1
+        return out
+
+
 class PhiloxState:
     """CUDA-graph-safe state for in-kernel noise: a device vector ``{seed, base offset}`` the step kernels read at RUN time
     (``mixgrpo_philox_args.device_state``).  A launch captured into a graph keeps only its position relative to the base
@@ -189,7 +237,8 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                sde_solver: bool = True, out_x_next: Optional[torch.Tensor] = None, want_x0: bool = True,
                want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
                out_logp: Optional[torch.Tensor] = None, philox=None,
-               out_x0: Optional[torch.Tensor] = None, early: int = 0, decode: Optional[dict] = None):
+               out_x0: Optional[torch.Tensor] = None, early: int = 0, decode: Optional[dict] = None,
+               defer: Optional[Tuple[int, int]] = None):
     """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
     requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in.
 
@@ -197,7 +246,9 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     ``early``: 1 = model output / noise were not written by the immediately preceding launch on this stream
     (MIXGRPO_FLAG_PDL_EARLY_V), 2 = no streamed input was (MIXGRPO_FLAG_PDL_EARLY_LOADS).
     ``decode``: ``{"out": fp32 (B,C,H,W), "divisor": 0.3611, "shift": 0.1159, "from_x0": False, "reciprocal": False}`` —
-    the VAE's input (unpack + de-normalise, TR:102-115, TR:286-287) written by this launch as a second output."""
+    the VAE's input (unpack + de-normalise, TR:102-115, TR:286-287) written by this launch as a second output.
+    ``defer``: ``DeferredLogProbs.slot(i, coefs)`` — the launch only accumulates its log-prob sums there (no log-prob is
+    returned; ``want_logp`` is ignored)."""
     global launch_count
     tb = binding()
     if tb is not None:                                    # compiled binding: same checks, same C-ABI call, no interpreter time
@@ -208,17 +259,23 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                 off, state = int(philox[1]) & 0xFFFFFFFFFFFFFFFF, philox[0].state.data_ptr()
             else:
                 seed, off = int(philox[0]) & 0xFFFFFFFFFFFFFFFF, int(philox[1]) & 0xFFFFFFFFFFFFFFFF
+        d_ptr, d_bytes = defer if defer is not None else (0, 0)
+        if defer is not None:
+            want_logp, out_logp = False, None
         if decode is None:
             res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
-                                want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, None, 1.0, 0.0, False, False)
+                                want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, None, 1.0, 0.0, False, False,
+                                d_ptr, d_bytes)
         else:
             res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
                                 want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, decode["out"],
                                 float(decode.get("divisor", 1.0)), float(decode.get("shift", 0.0)), bool(decode.get("from_x0", False)),
-                                bool(decode.get("reciprocal", False)))
+                                bool(decode.get("reciprocal", False)), d_ptr, d_bytes)
         launch_count += 1 if v.shape[0] else 0
         return res
     lib = _cabi.lib()
+    if defer is not None:
+        want_logp, out_logp = False, None
     _require_cuda(v, "model_output")
     _require_cuda(x, "latents")
     if x.dtype != torch.float32:
@@ -309,6 +366,8 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     st = _stream_ptr(dev)
     ws = _workspace(dev, B, n, st) if want_logp else None
     flags = (FLAG_ROUND_LIKE_TORCH if (round_like_torch and vd == BF16) else 0) | (FLAG_PDL_EARLY_LOADS if early == 2 else (FLAG_PDL_EARLY_V if early == 1 else 0))
+    if defer is not None:
+        flags |= FLAG_DEFER_LOGP
     ext = None
     if decode is not None:
         d_out = decode["out"]
@@ -320,8 +379,8 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
         keep.append(xe)
         ext = C.byref(xe)
     common_out = (out_p, out_bs, x0.data_ptr() if want_x0 else None, mean.data_ptr() if want_mean else None,
-                  logp.data_ptr() if want_logp else None, ws.data_ptr() if want_logp else None,
-                  ws.numel() if want_logp else 0, B, n, C.byref(coefs))
+                  logp.data_ptr() if want_logp else None, (defer[0] if defer is not None else (ws.data_ptr() if want_logp else None)),
+                  (defer[1] if defer is not None else (ws.numel() if want_logp else 0)), B, n, C.byref(coefs))
     with _on_device(dev):
         if family == FLOW:
             rc = lib.mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr(), x_bs, noise_p, in_p, in_bs, *common_out, src, flags, st, ext)

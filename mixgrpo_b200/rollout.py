@@ -53,6 +53,10 @@ class SamplerConfig:
     # anyway, exactly like the reference (SU:201-208 runs on every step); False skips the reduction on ODE steps (their CTAs
     # retire right after their stores: -0.5 us per launch at (12,4096,64)) and leaves NaN in those columns.
     ode_log_probs: bool = True
+    # The rollout's log-probs are only read once the rollout is over (SU:153-155): its step launches accumulate their per-sample
+    # sums with a fire-and-forget reduction and ONE finalize launch writes all_log_probs (mixgrpo_logp_finalize) — same packed
+    # integer sums, same bits, but no CTA waits an L2 round trip for a returning atomic before it retires.
+    defer_log_probs: bool = True
 
 
 def sigma_schedule(sampling_steps: int, shift: float, device=None) -> torch.Tensor:
@@ -101,8 +105,9 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
     B, dev = z.shape[0], z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
     _ops.cast_rows(z, traj[:, 0])
-    if cfg.ode_log_probs:
-        logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
+    acc = _ops.DeferredLogProbs(dev, n_steps, B, z[0].numel()) if (cfg.defer_log_probs and B > 0) else None
+    if cfg.ode_log_probs or acc is not None:
+        logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)                     # finalize also fills skipped rows with NaN
     else:
         logps_t = torch.full((n_steps, B), float("nan"), dtype=torch.float32, device=dev)       # skipped columns stay poisoned
     host_sig = _coefs.host_schedule(sigmas).tolist()
@@ -139,7 +144,7 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
             _, x0, _, _ = _ops.fused_step(_ops.DPM, v, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
                                           noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
                                           out_logp=logps_t[i] if lp_on else None, want_logp=lp_on, want_x0=True, round_like_torch=rnd,
-                                          early=early, decode=dec)
+                                          early=early, decode=dec, defer=acc.slot(i, k) if (acc is not None and lp_on) else None)
             dpm_state.update(x0)
             dpm_state.update_lower_order()
         else:
@@ -158,10 +163,12 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
             lp_on = (not determistic[i]) or cfg.ode_log_probs
             _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
                                           out_logp=logps_t[i] if lp_on else None, want_logp=lp_on, want_x0=keep_x0, round_like_torch=rnd,
-                                          early=early, decode=dec)
+                                          early=early, decode=dec, defer=acc.slot(i, k) if (acc is not None and lp_on) else None)
             if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
                 dpm_state.update(x0)
                 dpm_state.update_lower_order()
+    if acc is not None:
+        acc.finalize(logps_t)                                                # ONE launch: every step's log-probs
     if philox_state is not None:
         philox_state.advance()                                               # the next rollout (or graph replay) draws fresh noise
     z_final = traj[:, n_steps]

@@ -33,6 +33,9 @@ from ._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE, SRC_PHILOX
 #: supplies none; off by default so a drop-in run consumes torch's RNG stream exactly like torch.randn would
 INKERNEL_NOISE = os.environ.get("MIXGRPO_INKERNEL_NOISE", "0") == "1"
 
+#: run_sample_step: step launches only accumulate their log-prob sums, one finalize launch writes all_log_probs (same bits)
+DEFER_LOG_PROBS = os.environ.get("MIXGRPO_DEFER_LOG_PROBS", "1") == "1"
+
 #: rounding mode used when callers do not pass ``rounding=`` ("ref_cuda" | "ref_cpu" | "fp32")
 DEFAULT_ROUNDING = os.environ.get("MIXGRPO_ROUNDING", "ref_cuda")
 
@@ -404,6 +407,8 @@ def run_sample_step(
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
     _ops.cast_rows(z, traj[:, 0])
     logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)   # step-major so each kernel writes a row
+    # all_log_probs is read after the loop only (SU:153-155): the step launches accumulate, ONE finalize launch writes every row
+    acc = _ops.DeferredLogProbs(dev, n_steps, B, z[0].numel()) if (DEFER_LOG_PROBS and B > 0) else None
     mode = _mode(rounding)
     host_sig = _coefs.host_schedule(sigma_schedule)
     guidance = torch.tensor([3.5], device=dev, dtype=torch.bfloat16)
@@ -451,19 +456,19 @@ def run_sample_step(
                 nz = torch.randn(pred.shape, device=dev, dtype=torch.float32)
             _, pred_original, lp, _ = _ops.fused_step(_ops.DPM, pred, x, k, src=SRC_NOISE if sde else SRC_DETERMINISTIC,
                                                       noise=nz if sde else None, m1=m1, m2=m2, order=order, out_x_next=out,
-                                                      out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
+                                                      out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
             dpm_state.update(pred_original)
             dpm_state.update_lower_order()
         elif args.flow_grpo_sampling:
             k, _ = _coefs.flow(sigma_schedule, i, args.eta, mode, bf16_v)
             if determistic[i]:
                 _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_DETERMINISTIC, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
             else:
                 if nz is None:
                     nz = torch.randn(pred.shape, device=dev, dtype=pred.dtype)
                 _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_NOISE, noise=nz, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
             if flash:                                                               # SU:116-117, 127
                 dpm_state.update(pred_original)
                 dpm_state.update_lower_order()
@@ -471,14 +476,16 @@ def run_sample_step(
             k, _ = _coefs.dance(sigma_schedule, i, args.eta, mode, bf16_v)
             if determistic[i]:
                 _, pred_original, lp, _ = _ops.fused_step(_ops.DANCE, pred, x, k, src=SRC_DETERMINISTIC, sde_solver=False,
-                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
+                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
             else:
                 if nz is None:
                     nz = torch.randn(pred.shape, device=dev, dtype=torch.float32)
                 _, pred_original, lp, _ = _ops.fused_step(_ops.DANCE, pred, x, k, src=SRC_NOISE, noise=nz, sde_solver=True,
-                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec)
+                                                          out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
         cur = out
         steps_done += 1
+    if acc is not None:
+        acc.finalize(logps_t)
 
     z_out = traj[:, n_steps]
     latents = pred_original if args.drop_last_sample else z_out.to(pred_original.dtype)   # SU:149-152

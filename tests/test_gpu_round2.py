@@ -309,3 +309,89 @@ def test_rollout_without_ode_log_probs_changes_nothing_that_is_read(flash):
     assert torch.equal(a[3][:, window], b[3][:, window])
     ode = [i for i in range(a[3].shape[1]) if i not in window]
     assert torch.isnan(b[3][:, ode]).all() and torch.isfinite(a[3][:, [i for i in ode if i < a[3].shape[1] - 1]]).all()
+
+
+# ------------------------------------------------------------------------------------------ deferred log-prob finalization
+@pytest.mark.parametrize("family", ["flow", "dance", "flash", "dpm_all"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_deferred_log_probs_are_bit_identical_to_the_immediate_path(family, dtype):
+    """MIXGRPO_FLAG_DEFER_LOGP + mixgrpo_logp_finalize: the rollout's step launches only accumulate, ONE launch finalizes — the
+    same packed integer sums, so all_log_probs (and everything else) must not change by a bit; one launch more in total."""
+    from mixgrpo_b200 import ops, rollout as R
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(21)
+    B, S, N = 5, 320, 12                                # 160 tiles... n = 20480: 10 CTAs per sample
+    window = [2, 3, 4, 5]
+    kw = {"flow": {}, "dance": dict(flow_grpo_sampling=False), "flash": dict(dpm_algorithm_type="dpmsolver++", dpm_apply_strategy="post"),
+          "dpm_all": dict(dpm_algorithm_type="dpmsolver++", dpm_apply_strategy="all", dpm_solver_order=3)}[family]
+    z0 = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    vs = [torch.randn(B, S, 64, device=d, generator=g).to(dtype) for _ in range(N)]
+    nd = dtype if family in ("flow", "flash") else torch.float32
+    nz = [torch.randn(B, S, 64, device=d, generator=g).to(nd) if i in window else None for i in range(N)]
+    det = R.window_mask(N, window)
+    sig = R.sigma_schedule(N, 3.0)
+    before = ops.launch_count
+    a = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N, defer_log_probs=False, **kw), noises=nz)
+    n_imm = ops.launch_count - before
+    before = ops.launch_count
+    b = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N, defer_log_probs=True, **kw), noises=nz)
+    assert ops.launch_count - before == n_imm + 1
+    assert torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
+    assert torch.equal(torch.nan_to_num(a[3], nan=123.0), torch.nan_to_num(b[3], nan=123.0))      # the last DPM step's NaN (sigma_t = 0) included
+    # twice in a row on the same cached records: finalize left them zeroed
+    c = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N, **kw), noises=nz)
+    assert torch.equal(torch.nan_to_num(c[3], nan=123.0), torch.nan_to_num(a[3], nan=123.0))
+
+
+def test_deferred_log_probs_far_samples_inactive_rows_and_graph_replay():
+    from mixgrpo_b200 import coefs, ops
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN
+    d = _dev()
+    g = torch.Generator().manual_seed(8)
+    B, S, idx = 3, 256, 7
+    x = torch.randn(B, S, 64, generator=g)
+    v = torch.randn(B, S, 64, generator=g)
+    _, _, _, mean, scale = O.flow_step(v, x, ETA, SIG, idx, x)
+    xn = mean + 1000.0 * scale * torch.randn(B, S, 64, generator=g)     # shares beyond the packed field: side accumulators, deferred
+    xn[1, :32] += 50 * 1000.0 * scale
+    ref = O.flow_step(v, x, ETA, SIG, idx, xn)[2]
+    k, _ = coefs.flow(SIG, idx, ETA, "fp32", False)
+    vd, xd, xnd = v.to(d), x.to(d), xn.to(d)
+    out = torch.zeros(3, B, device=d)
+
+    def run():
+        acc = ops.DeferredLogProbs(d, 3, B, S * 64)
+        ops.fused_step(ops.FLOW, vd, xd, k, src=SRC_GIVEN, x_next=xnd, want_x0=False, defer=acc.slot(0, k))
+        ops.fused_step(ops.FLOW, vd, xd, k, src=SRC_DETERMINISTIC, want_x0=False, defer=acc.slot(2, k))      # launch 1 never takes a slot
+        acc.finalize(out)
+
+    run()
+    imm = ops.fused_step(ops.FLOW, vd, xd, k, src=SRC_GIVEN, x_next=xnd, want_x0=False)[2]
+    assert torch.equal(out[0], imm) and torch.allclose(out[0].cpu(), ref, rtol=1e-4, atol=0)
+    assert torch.isnan(out[1]).all()
+    assert torch.equal(out[2], ops.fused_step(ops.FLOW, vd, xd, k, src=SRC_DETERMINISTIC, want_x0=False)[2])
+    want = out.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            run()
+        for _ in range(3):
+            out.zero_()
+            gr.replay()
+            s.synchronize()
+            assert torch.equal(torch.nan_to_num(out, nan=5.0), torch.nan_to_num(want, nan=5.0))
+    torch.cuda.current_stream().wait_stream(s)
+    with pytest.raises(ValueError):
+        ops.DeferredLogProbs(d, 3, B, S * 64).finalize(torch.zeros(2, B, device=d))
+    with pytest.raises(RuntimeError):      # the fused loss needs its log-prob inside the launch: the flag is refused there
+        from mixgrpo_b200 import _cabi
+        import ctypes as C
+        la = _cabi.LossArgs()
+        la.old_logp, la.advantages = out[0].data_ptr(), out[0].data_ptr()
+        ws = torch.zeros(4096, dtype=torch.uint8, device=d)
+        rc = _cabi.lib().mixgrpo_policy_fwd(0, vd.data_ptr(), 0, xd.data_ptr(), S * 64, xnd.data_ptr(), S * 64, out[1].data_ptr(), ws.data_ptr(), ws.numel(), B,
+                                            S * 64, C.byref(k), C.byref(la), _cabi.FLAG_DEFER_LOGP, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "policy_fwd")
