@@ -365,18 +365,21 @@ def measure_kernels(dev, peak_gbs, B=12, S=4096, full=True):
         return lambda: [fn(i) for i in range(ns)]
 
     common = dict(round_like_torch=True, early=1)
-    # as the rollout launches them: the step only accumulates its log-prob sums (MIXGRPO_FLAG_DEFER_LOGP) and ONE finalize launch
-    # per rollout writes every step's log-probs — here one finalize per 10 step launches, inside the timed graph
-    acc = ops.DeferredLogProbs(dev, ns, B, S * C)
+    # as the rollout launches them: a step only accumulates its log-prob sums (MIXGRPO_FLAG_DEFER_LOGP) and ONE finalize launch
+    # per rollout writes every step's log-probs — here, like a rollout, 25 step launches (cycling through the buffer sets: a set
+    # comes round again only after > 126 MB of other traffic) + 1 finalize inside the timed graph, divided by 25
+    nl = N_STEPS
+    acc = ops.DeferredLogProbs(dev, nl, B, S * C)
+    lp25 = torch.empty(nl, B, device=dev)
     def deferred(fn):
         def run():
-            for i in range(ns):
-                fn(i)
-            acc.finalize(lps)
+            for j in range(nl):
+                fn(j % ns, j)
+            acc.finalize(lp25)
         return run
-    rec("ode", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_x0=False, defer=acc.slot(i, k), **common)), ns, s), "ode")
-    rec("sde", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=False, defer=acc.slot(i, k), **common)), ns, s), "sde")
-    rec("sde_x0", _time_graph(deferred(lambda i: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=True, out_x0=x0s[i], defer=acc.slot(i, k), **common)), ns, s), "sde_x0")
+    rec("ode", _time_graph(deferred(lambda i, j: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_x0=False, defer=acc.slot(j, k), **common)), nl, s), "ode")
+    rec("sde", _time_graph(deferred(lambda i, j: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=False, defer=acc.slot(j, k), **common)), nl, s), "sde")
+    rec("sde_x0", _time_graph(deferred(lambda i, j: ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=True, out_x0=x0s[i], defer=acc.slot(j, k), **common)), nl, s), "sde_x0")
     if not full:
         return res
     # the window's policy update as the step launches it: 4 forwards in ONE launch, 4 backwards in ONE launch
@@ -428,11 +431,11 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     tot_b = sum(res[k]["bytes_per_elem"] * e * c for k, c, _ in plan)
     tot_us = sum(res[k]["us_per_launch"] * c for k, c, _ in plan)
     roof = {"bound": "hbm",
-            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 30 launches and the largest share of its device time; launched as the rollout launches it (log-prob sums accumulated, one finalize launch per rollout — included in the time, one per 10 launches here)",
+            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 30 launches and the largest share of its device time; launched as the rollout launches it (log-prob sums accumulated, one finalize launch per 25 step launches, its time included)",
             "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
             "unit": "GB/s", "frac": round(top["GBps"] / peak_gbs, 4), "traffic": None, "us_per_launch": top["us_per_launch"],
             "algorithmic_bytes_per_launch": e * bytes_per_elem("ode", False),
-            "how": "CUDA events around 20 replays of a 10-launch CUDA graph over rotating buffer sets (10 x (6.3 + 12.6 + 12.6) MB > L2), launched as the step launches it (PDL, model-output loads ahead of the wait)",
+            "how": "CUDA events around 20 replays of a CUDA graph of 25 launches + 1 finalize cycling through 10 buffer sets (10 x (6.3 + 12.6 + 12.6) MB > L2: every input is cold), launched as the step launches it (PDL, model-output loads ahead of the wait, deferred log-prob finalization)",
             "step_weighted": {"achieved": round(tot_b / tot_us / 1e3, 1), "frac": round(tot_b / tot_us / 1e3 / peak_gbs, 4), "bytes": tot_b, "us": round(tot_us, 2),
                               "what": "all 27 streaming launches of a headline step (21 ode, 4 sde, window forward x4, window backward x4), each at its isolated cold-input time"}}
     return roof, res

@@ -151,6 +151,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// second stage of the CTA reduction: lanes 0..7 hold the 8 warp sums, the other lanes exact zeros — the xor-16 and xor-8
+// levels of warp_sum would only add those zeros, so three levels give the same bits
+static_assert(kThreads / 32 == 8, "warp_sum8 assumes 8 warps per CTA");
+__device__ __forceinline__ float warp_sum8(float v) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 // ---------------------------------------------------------------- clipped-ratio GRPO loss, one sample
 // TR:560-583 for ONE log-prob (TR = fastvideo/train_grpo_flux.py).  Shared by the batch loss kernel and by the

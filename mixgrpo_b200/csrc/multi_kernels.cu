@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   __syncthreads();
   if (warp != 0) return;
   float t = lane < kThreads / 32 ? s_warp[lane] : 0.f;
-  t = warp_sum(t);
+  t = warp_sum8(t);
   if (lane == 0) {
     const int ctas = gridDim.x;
     const float r = __fdiv_rn(t, __fmul_rn((float)n, q.k.two_var));

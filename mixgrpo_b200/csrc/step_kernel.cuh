@@ -200,7 +200,7 @@ step_kernel(const __grid_constant__ StepParams p) {
   __syncthreads();
   if (warp != 0) return;                           // warps 1..7 are done: nothing waits on the atomic
   float t = lane < kThreads / 32 ? s_warp[lane] : 0.f;
-  t = warp_sum(t);
+  t = warp_sum8(t);
   if (lane == 0) {
     const int ctas = gridDim.x;
     const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
