@@ -241,7 +241,12 @@ def native_step(w: Workload, v_list=None, eps=None, rewards=None, group=None, co
         # joined before the policy updates need the advantages.  No NCCL anywhere in the step.
         w.px_stream.wait_stream(cur0)
         with torch.cuda.stream(w.px_stream):
+            from mixgrpo_b200 import ops
             adv, w.gathered = w.px.gather_advantages(rew, B, w.weights)
+            # the previous step's stats rows are reduced one step late, off the critical path: snapshot them (one tiny launch of
+            # ours) before this step's policy update overwrites them — ONE graph serves every step (two alternating graphs with
+            # their own buffers cost 6.7 us per step: measured at N = 1, profiles/r02_scaling.md)
+            ops.cast_rows(w.stats_rows.view(1, -1), w.prev_rows.view(1, -1))
             w.px.allreduce_stats(w.prev_rows.view(-1))
     det = R.window_mask(N_STEPS, window)
     nz = [None] * N_STEPS
@@ -714,10 +719,10 @@ def run_native(args):
         w.px = px_check if peer_mode else None
     graph, (stats, logps, _, adv_graph), coll_in_graph, launches = capture_step(w, comm_stream if args.collectives == "graph" else None)
     coll_in_graph = coll_in_graph or peer_mode
-    # two graphs with their own stats rows, used alternately, so step k+1 never has to wait for step k's all-reduce to
-    # finish reading its rows — the logging reduction overlaps the next step completely
+    # --collectives eager only: two graphs with their own stats rows, used alternately, so step k+1 never has to wait for step
+    # k's NCCL all-reduce to finish reading its rows (peer mode snapshots the rows inside its single graph instead)
     graphs, rows = [graph], [w.stats_rows]
-    if world > 1 and (peer_mode or not coll_in_graph):
+    if (world > 1 and not coll_in_graph and args.collectives != "none") or os.environ.get("MIXGRPO_BENCH_TWO_GRAPHS") == "1":
         w.stats_rows, w.prev_rows = w.prev_rows, w.stats_rows
         g2, _, _, _ = capture_step(w, None)
         graphs.append(g2)
@@ -728,10 +733,10 @@ def run_native(args):
     def step():
         k = counter[0] % len(graphs)
         counter[0] += 1
-        if world > 1 and not coll_in_graph:
+        if world > 1 and not coll_in_graph and args.collectives != "none":
             main_stream.wait_event(done[k])          # the collectives that read rows[k] two steps ago
         graphs[k].replay()
-        if world > 1 and not coll_in_graph:
+        if world > 1 and not coll_in_graph and args.collectives != "none":
             comm_stream.wait_stream(main_stream)
             with torch.cuda.stream(comm_stream):
                 dist.all_gather_into_tensor(w.gbuf, w.rewards)
@@ -754,7 +759,7 @@ def run_native(args):
                 w.px.allreduce_stats(rows[(counter[0] - 1) % len(graphs)].view(-1))   # the last step's sums (earlier ones were reduced one step late)
             elif coll_in_graph:
                 dist.all_reduce(w.stats_rows, op=dist.ReduceOp.AVG)
-            else:
+            elif args.collectives != "none":
                 main_stream.wait_stream(comm_stream)  # the last step's collectives end inside the timed region
         b.record()
         torch.cuda.synchronize(dev)
@@ -842,7 +847,7 @@ def run_native(args):
     if rank == 0:
         coll = ("none (N=1)" if world == 1 else
                 "fused peer-memory kernels inside the step graph, no NCCL: reward gather + advantages (1 launch; 64-bit {call,value} words pushed into the peers' memory over NVLink), "
-                "[4x12x4] stats all-reduce of the previous step (1 launch), both on a side branch of the graph" if peer_mode else
+                "[4x12x4] stats all-reduce of the previous step (snapshot + all-reduce: 2 launches), all on a side branch of the graph" if peer_mode else
                 "1 all_gather_into_tensor [3x12 f32] + 1 all_reduce [4x12x4 f32] per step, " +
                 ("captured in the step graph on a side branch" if coll_in_graph else "eager on a side stream, double-buffered stats rows"))
         line = {
@@ -865,7 +870,7 @@ def run_native(args):
                     "ceiling_how": "tools/h2d_ceiling.py method: plain pinned cudaMemcpyAsync of h2d_bytes_per_step per rank, all ranks at once; better of the best single copy of 5 and 5 back-to-back",
                     "upload": f"{args.e2e_chunks} cudaMemcpyAsync of one pinned block per step, double-buffered across steps",
                     "api": "mixgrpo_b200.rollout.rollout + grpo.compute_group_advantages (peer.PeerExchange.gather_advantages at N > 1) + rollout.policy_update_window, eager launches"},
-            "gpu_launches": (launches + (1 if peer_mode else 0)) * args.steps,
+            "gpu_launches": launches * args.steps + (1 if peer_mode else 0),
             "launches_per_step": launches,
             "clocks": clk.summary(), "roofline": roof, "kernels": kernels, "kernels_by_group_size": curve, "configs": configs, "cpu_baseline": cpu,
             "check": check,
@@ -1039,8 +1044,8 @@ def main():
                     help="which BASELINE config is the line's headline workload (default configs[1]; the default line also carries the others under `configs`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[3] / configs[4] lines")
-    ap.add_argument("--collectives", default="peer", choices=["peer", "graph", "eager"],
-                    help="N>1: 'peer' = fused peer-memory kernels in the step graph (no NCCL); 'graph' = the two NCCL collectives captured in the step graph; 'eager' = NCCL on a side stream")
+    ap.add_argument("--collectives", default="peer", choices=["peer", "graph", "eager", "none"],
+                    help="N>1 ('none' = tuning only: no exchange at all, to separate the exchange's cost from the multi-process environment's): 'peer' = fused peer-memory kernels in the step graph (no NCCL); 'graph' = the two NCCL collectives captured in the step graph; 'eager' = NCCL on a side stream")
     ap.add_argument("--policy", default="window", choices=["window", "pair", "single"],
                     help="window update as 2 launches for all 4 steps (default), as 4 x (forward, backward) on parallel branches, or the single-pass kernel per step")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="cudaMemcpyAsync calls per e2e step upload (1 = one 157 MB copy; 25 = one per model output)")
