@@ -239,8 +239,10 @@ def native_step(w: Workload, v_list=None, eps=None, rewards=None, group=None, co
         # The path's single exchange AND the advantages as ONE kernel over NVLink peer memory, plus the PREVIOUS step's
         # logging sums as one all-reduce kernel (csrc/peer_kernels.cu) — on a side branch concurrent with the rollout,
         # joined before the policy updates need the advantages.  No NCCL anywhere in the step.
-        w.px_stream.wait_stream(cur0)
-        with torch.cuda.stream(w.px_stream):
+        px_place = os.environ.get("MIXGRPO_BENCH_PX_PLACE", "side")            # tuning: side branch | head of the main chain
+        if px_place == "side":
+            w.px_stream.wait_stream(cur0)
+        with torch.cuda.stream(w.px_stream if px_place == "side" else cur0):
             from mixgrpo_b200 import ops
             adv, w.gathered = w.px.gather_advantages(rew, B, w.weights)
             # the previous step's stats rows are reduced one step late, off the critical path: snapshot them (one tiny launch of
@@ -254,7 +256,8 @@ def native_step(w: Workload, v_list=None, eps=None, rewards=None, group=None, co
         nz[i] = (eps if eps is not None else w.eps)[j]
     _, _, traj, logps, sig_used = R.rollout(lambda lat, s, i: v_list[i], w.z0, w.sig, det, w.cfg, noises=nz)
     if w.px is not None:
-        cur0.wait_stream(w.px_stream)
+        if os.environ.get("MIXGRPO_BENCH_PX_PLACE", "side") == "side":
+            cur0.wait_stream(w.px_stream)
     else:
         if collectives and dist.is_initialized() and dist.get_world_size() > 1:
             gathered = grpo.gather_rewards(rew, group)                      # the path's single exchange
@@ -697,6 +700,9 @@ def run_native(args):
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     peer_mode = world > 1 and args.collectives == "peer"
     px_check = None
+    if world == 1 and os.environ.get("MIXGRPO_BENCH_PEER_N1") == "1":          # tuning: the exchange kernels with no peer
+        from mixgrpo_b200.peer import PeerExchange
+        w.px = PeerExchange()
     if world > 1:
         from mixgrpo_b200.peer import PeerExchange
         mixgrpo_b200._cabi.lib().mixgrpo_set_tuning(2, 60000)      # a lost peer fails the bench after 60 s instead of 10 min
