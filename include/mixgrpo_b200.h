@@ -162,6 +162,13 @@ typedef struct mixgrpo_step_ext {
   int from_x0;
   int reciprocal;   /* 0: true division (what torch computes on CPU tensors); 1: src * (1.0f / divisor), which is what torch's CUDA
                        div-by-python-scalar kernel computes (one rounding more; differs from true division by <= 1 ulp) */
+  /* Trajectory seed (nullable x_f32_out; flow family, vector path, not together with decode_out): the rollout's FIRST step
+   * takes `x` as the bf16 initial latent z itself (the `x` argument is then a bf16 pointer, x_bs in elements) and also writes
+   * its fp32 widening — all_latents[:, 0], what SU:26 / SU:153's torch.stack promotion produces — to x_f32_out (batch stride
+   * x_f32_out_bs): no separate cast launch, and z is read once as 2 B/elem instead of once as 2 and once more as 4. */
+  int x_is_bf16;
+  float* x_f32_out;
+  int64_t x_f32_out_bs;
 } mixgrpo_step_ext;
 
 int mixgrpo_flow_step(const void* v, int v_dtype, const float* x, int64_t x_bs,

@@ -37,7 +37,8 @@ class PhiloxArgs(C.Structure):
 class StepExt(C.Structure):
     """mirror of ``mixgrpo_step_ext`` (include/mixgrpo_b200.h): the decode-ready second output of a step launch."""
     _fields_ = [("decode_out", C.c_void_p), ("C", C.c_int), ("H", C.c_int), ("W", C.c_int), ("divisor", C.c_float),
-                ("shift", C.c_float), ("from_x0", C.c_int), ("reciprocal", C.c_int)]
+                ("shift", C.c_float), ("from_x0", C.c_int), ("reciprocal", C.c_int), ("x_is_bf16", C.c_int), ("x_f32_out", C.c_void_p),
+                ("x_f32_out_bs", C.c_int64)]
 
 
 class LossArgs(C.Structure):

@@ -45,6 +45,9 @@ struct StepParams {
   float* decode_out;
   int dC, dH, dW, d_from_x0, d_recip;
   float d_div, d_shift;
+  // optional trajectory seed: x is the bf16 initial latent; its fp32 widening is also written here (all_latents[:, 0])
+  float* seed_out;
+  long long seed_bs;
 };
 
 // (B, S, 4C) packed scalars [i, i+8) of sample b -> (B, C, H, W): two channels x (2 x 2) patch = four 8-byte stores; a warp's
@@ -114,10 +117,11 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
 }
 
 // OUT (compile time): 0 = neither x0 nor mean is stored (the rollout driver's steps: x0 is dead code), 1 = x0, 2 = x0 + mean
-// DEC (compile time): also emit the decode-ready tensor (mixgrpo_step_ext) — its own instantiations, so the 24 steps of a
+// EXT (compile time): 0 none; 1 also emit the decode-ready tensor; 2 trajectory seed (x read as bf16, its fp32 widening stored
+// too) — mixgrpo_step_ext; their own instantiations, so the other steps of a
 // rollout that do not need it keep their register budget
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, bool DEC>
-__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE) || DEC || SRC == MIXGRPO_SRC_PHILOX) ? 4 : 6)
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, int EXT>
+__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE) || EXT == 1 || SRC == MIXGRPO_SRC_PHILOX) ? 4 : 6)
 step_kernel(const __grid_constant__ StepParams p) {
   // Programmatic dependent launch: inputs the immediately preceding launch cannot have written are requested BEFORE
   // griddepcontrol.wait, so their DRAM latency overlaps that launch's drain (MIXGRPO_FLAG_PDL_EARLY_V / _EARLY_LOADS)
@@ -137,7 +141,8 @@ step_kernel(const __grid_constant__ StepParams p) {
     load_tile<VT, VECTOR>(vp, off, n, v);
     if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
     if (p.early == 1) pdl_prologue();
-    load_tile<float, VECTOR>(xp, off, n, x);
+    if constexpr (EXT == 2) load_tile<__nv_bfloat16, VECTOR>(reinterpret_cast<const __nv_bfloat16*>(p.x) + (long long)b * p.x_bs, off, n, x);
+    else load_tile<float, VECTOR>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_PHILOX) {     // draw the noise here: element e -> component e%4 of Philox(e/4)
       unsigned long long ph_seed = p.philox_seed, ph_off = p.philox_offset;
       if (p.philox_state) { ph_seed = __ldg(p.philox_state); ph_off += __ldg(p.philox_state + 1); }   // graph-safe state
@@ -186,7 +191,8 @@ step_kernel(const __grid_constant__ StepParams p) {
     }
     if constexpr (OUT >= 1) store_tile<VECTOR>(p.x0_out + (long long)b * n, off, n, x0);
     if constexpr (OUT == 2) store_tile<VECTOR>(p.mean_out + (long long)b * n, off, n, mu);
-    if constexpr (DEC) {                           // the rollout's last step: the VAE's input leaves from the same registers
+    if constexpr (EXT == 2) store_tile<VECTOR>(p.seed_out + (long long)b * p.seed_bs, off, n, x);   // all_latents[:, 0] = float(z)
+    if constexpr (EXT == 1) {                      // the rollout's last step: the VAE's input leaves from the same registers
       if constexpr (OUT >= 1) { if (p.d_from_x0) store_decoded(p, b, off + threadIdx.x * kVec, x0); else store_decoded(p, b, off + threadIdx.x * kVec, xn); }
       else store_decoded(p, b, off + threadIdx.x * kVec, xn);
     }
@@ -241,24 +247,28 @@ extern int g_max_ctas_per_sample;                       // bench knob (mixgrpo_s
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, bool DEC>
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, int EXT>
 static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
   if (ctas != p.tiles || !VECTOR) p.early = 0;           // early loads assume one tile per CTA (no loop-carried state in the kernel)
   dim3 grid((unsigned)ctas, (unsigned)p.B);
-  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT, DEC>, grid, kThreads, 0, st, p);
+  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT, EXT>, grid, kThreads, 0, st, p);
   return (int)cudaGetLastError();
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, int OUT>
 static int pick_vec(StepParams& p, bool vec_ok, cudaStream_t st) {
+  if (p.seed_out) {                                        // set_ext() admitted it: vector path, bf16 x
+    if constexpr (FAM == kFlow && SRC != MIXGRPO_SRC_GIVEN && OUT <= 1) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, 2>(p, st);
+    else return MIXGRPO_EUNSUPPORTED;                      // the flow family's rollout steps only
+  }
   if (p.decode_out) {                                      // set_ext() admitted it: vector path, a computed x_next (or x0)
-    if constexpr (SRC != MIXGRPO_SRC_GIVEN && OUT <= 1) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, true>(p, st);
+    if constexpr (SRC != MIXGRPO_SRC_GIVEN && OUT <= 1) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, 1>(p, st);
     else return MIXGRPO_EUNSUPPORTED;                      // not together with the mean output
   }
-  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, OUT, false>(p, st);
-  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, false>(p, st);
+  if (!vec_ok) return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, false, OUT, 0>(p, st);
+  return launch<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, 0>(p, st);
 }
 
 template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE>
@@ -316,6 +326,7 @@ static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};
   p.early = 0; p.defer = 0;
   p.decode_out = nullptr; p.dC = p.dH = p.dW = p.d_from_x0 = p.d_recip = 0; p.d_div = 1.f; p.d_shift = 0.f;
+  p.seed_out = nullptr; p.seed_bs = 0;
 }
 
 static inline void set_philox(StepParams& p, const void* noise_host) {
@@ -331,7 +342,15 @@ static inline void set_early(StepParams& p, unsigned flags) {
 
 // validates and installs the optional decode output; returns 0 or a MIXGRPO_E* code
 static inline int set_ext(StepParams& p, const mixgrpo_step_ext* ext, int64_t n, bool vec, int src) {
-  if (!ext || !ext->decode_out) return 0;
+  if (!ext) return 0;
+  if (ext->x_f32_out) {                                    // trajectory seed: x is bf16 (16-B aligned is enough: vector_ok asked for 32)
+    if (!ext->x_is_bf16 || ext->decode_out || src == MIXGRPO_SRC_GIVEN) return MIXGRPO_EINVAL;
+    if (!vec || !aligned(ext->x_f32_out, 32) || (ext->x_f32_out_bs % kVec) != 0 || ext->x_f32_out_bs < n) return MIXGRPO_EUNSUPPORTED;
+    p.seed_out = ext->x_f32_out; p.seed_bs = ext->x_f32_out_bs;
+    return 0;
+  }
+  if (ext->x_is_bf16) return MIXGRPO_EINVAL;               // a bf16 x is only understood together with its fp32 copy-out
+  if (!ext->decode_out) return 0;
   if (ext->C <= 0 || ext->H <= 0 || ext->W <= 0 || (ext->C % 2) || (ext->H % 2) || (ext->W % 2) || (int64_t)ext->C * ext->H * ext->W != n ||
       !(ext->divisor != 0.f)) return MIXGRPO_EINVAL;
   if (ext->from_x0 ? !p.x0_out : (src == MIXGRPO_SRC_GIVEN)) return MIXGRPO_EINVAL;   // the decoded tensor must be one this launch computes

@@ -103,10 +103,16 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
                         const OptT& m1_o, const OptT& m2_o, int order, bool sde_solver, const OptT& out_x_next, bool want_x0, bool want_mean,
                         bool want_logp, bool rnd, const OptT& out_logp, const OptT& out_x0, int early, bool has_philox, uint64_t ph_seed,
                         uint64_t ph_offset, uint64_t ph_state, const OptT& decode_out, double divisor, double shift, bool from_x0,
-                        bool reciprocal, uint64_t defer_ptr = 0, int64_t defer_bytes = 0) {
+                        bool reciprocal, uint64_t defer_ptr = 0, int64_t defer_bytes = 0, const OptT& seed_out = c10::nullopt) {
   require_cuda(v, "model_output");
   require_cuda(x, "latents");
-  x = as_f32(x);
+  if (seed_out) {   // trajectory seed: x stays bf16 (the initial latent itself), its fp32 widening is written to seed_out as well
+    if (decode_out || x.scalar_type() != at::kBFloat16 || !x.is_contiguous() || seed_out->scalar_type() != at::kFloat ||
+        seed_out->sizes() != x.sizes() || !inner_contiguous(*seed_out))
+      fail_value("seed_out needs a contiguous bf16 `latents`, an fp32 view of the same shape, and no decode output");
+  } else {
+    x = as_f32(x);
+  }
   const int vd = dtype_code(v, "model_output");
   if (v.sizes() != x.sizes()) fail_value("model_output and latents differ in shape");
   if (!v.is_contiguous()) v = v.contiguous();
@@ -122,8 +128,8 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
     return o;
   }
   const int64_t n = v.numel() / B;
-  int64_t x_bs;
-  std::tie(x, x_bs) = rows(x, "latents");
+  int64_t x_bs = n;
+  if (!seed_out) std::tie(x, x_bs) = rows(x, "latents");
   const void* noise_p = nullptr;
   const float *in_p = nullptr, *m1_p = nullptr, *m2_p = nullptr;
   int64_t in_bs = n;
@@ -208,6 +214,11 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
       fail_value("decode['out'] must be a contiguous fp32 (B, C, H, W) tensor with C*H*W == elements per sample");
     xe.decode_out = d.data_ptr<float>(); xe.C = (int)d.size(1); xe.H = (int)d.size(2); xe.W = (int)d.size(3);
     xe.divisor = (float)divisor; xe.shift = (float)shift; xe.from_x0 = from_x0 ? 1 : 0; xe.reciprocal = reciprocal ? 1 : 0;
+    xe.x_is_bf16 = 0; xe.x_f32_out = nullptr; xe.x_f32_out_bs = 0;
+    ext = &xe;
+  } else if (seed_out) {
+    xe.decode_out = nullptr; xe.C = xe.H = xe.W = 0; xe.divisor = 1.f; xe.shift = 0.f; xe.from_x0 = 0; xe.reciprocal = 0;
+    xe.x_is_bf16 = 1; xe.x_f32_out = seed_out->data_ptr<float>(); xe.x_f32_out_bs = B > 1 ? seed_out->stride(0) : n;
     ext = &xe;
   }
   float* x0_p = want_x0 ? o.x0.data_ptr<float>() : nullptr;
@@ -217,13 +228,13 @@ StepOut fused_step_impl(int family, Tensor v, Tensor x, const mixgrpo_step_coefs
   const int64_t ws_n = defer_ptr ? defer_bytes : (want_logp ? ws.numel() : 0);
   int rc;
   if (family == kFlow)
-    rc = mixgrpo_flow_step(v.data_ptr(), vd, x.data_ptr<float>(), x_bs, noise_p, in_p, in_bs, out_p, out_bs, x0_p, mean_p, lp_p, ws_p, ws_n, B, n, &k,
+    rc = mixgrpo_flow_step(v.data_ptr(), vd, reinterpret_cast<const float*>(x.data_ptr()), x_bs, noise_p, in_p, in_bs, out_p, out_bs, x0_p, mean_p, lp_p, ws_p, ws_n, B, n, &k,
                            src, flags, st, ext);
   else if (family == kDance)
-    rc = mixgrpo_dance_step(v.data_ptr(), vd, x.data_ptr<float>(), x_bs, static_cast<const float*>(noise_p), in_p, in_bs, out_p, out_bs, x0_p, mean_p,
+    rc = mixgrpo_dance_step(v.data_ptr(), vd, reinterpret_cast<const float*>(x.data_ptr()), x_bs, static_cast<const float*>(noise_p), in_p, in_bs, out_p, out_bs, x0_p, mean_p,
                             lp_p, ws_p, ws_n, B, n, &k, src, sde_solver ? 1 : 0, flags, st, ext);
   else if (family == kDpm)
-    rc = mixgrpo_dpm_step(v.data_ptr(), vd, x.data_ptr<float>(), x_bs, static_cast<const float*>(noise_p), m1_p, m2_p, order, out_p, out_bs, x0_p, mean_p,
+    rc = mixgrpo_dpm_step(v.data_ptr(), vd, reinterpret_cast<const float*>(x.data_ptr()), x_bs, static_cast<const float*>(noise_p), m1_p, m2_p, order, out_p, out_bs, x0_p, mean_p,
                           lp_p, ws_p, ws_n, B, n, &k, src, flags, st, ext);
   else
     fail_value("unknown operator family");
@@ -339,10 +350,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         [](int family, const Tensor& v, const Tensor& x, uint64_t coefs_addr, int src, const OptT& noise, const OptT& x_next, const OptT& m1, const OptT& m2,
            int order, bool sde_solver, const OptT& out_x_next, bool want_x0, bool want_mean, bool want_logp, bool rnd, const OptT& out_logp,
            const OptT& out_x0, int early, bool has_philox, uint64_t ph_seed, uint64_t ph_offset, uint64_t ph_state, const OptT& decode_out, double divisor,
-           double shift, bool from_x0, bool reciprocal, uint64_t defer_ptr, int64_t defer_bytes) {
+           double shift, bool from_x0, bool reciprocal, uint64_t defer_ptr, int64_t defer_bytes, const OptT& seed_out) {
           StepOut o = fused_step_impl(family, v, x, coefs_at(coefs_addr), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
                                       want_logp && !defer_ptr, rnd, out_logp, out_x0, early, has_philox, ph_seed, ph_offset, ph_state, decode_out, divisor,
-                                      shift, from_x0, reciprocal, defer_ptr, defer_bytes);
+                                      shift, from_x0, reciprocal, defer_ptr, defer_bytes, seed_out);
           return py::make_tuple(opt(o.x_next), opt(o.x0), opt(o.logp), opt(o.mean));
         });
 

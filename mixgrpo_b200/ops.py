@@ -238,7 +238,7 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                want_mean: bool = False, want_logp: bool = True, round_like_torch: bool = False,
                out_logp: Optional[torch.Tensor] = None, philox=None,
                out_x0: Optional[torch.Tensor] = None, early: int = 0, decode: Optional[dict] = None,
-               defer: Optional[Tuple[int, int]] = None):
+               defer: Optional[Tuple[int, int]] = None, seed_out: Optional[torch.Tensor] = None):
     """One fused sampler step + log-prob launch.  Returns (x_next, x0, logp, mean); entries not
     requested are None; with ``src == SRC_GIVEN`` x_next is the tensor passed in.
 
@@ -248,7 +248,9 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     ``decode``: ``{"out": fp32 (B,C,H,W), "divisor": 0.3611, "shift": 0.1159, "from_x0": False, "reciprocal": False}`` —
     the VAE's input (unpack + de-normalise, TR:102-115, TR:286-287) written by this launch as a second output.
     ``defer``: ``DeferredLogProbs.slot(i, coefs)`` — the launch only accumulates its log-prob sums there (no log-prob is
-    returned; ``want_logp`` is ignored)."""
+    returned; ``want_logp`` is ignored).
+    ``seed_out``: the rollout's first step — ``x`` is the bf16 initial latent itself and its fp32 widening (``all_latents[:, 0]``,
+    SU:26 / SU:153) is written to this fp32 view as well: no separate cast launch (flow family; see ``can_seed``)."""
     global launch_count
     tb = binding()
     if tb is not None:                                    # compiled binding: same checks, same C-ABI call, no interpreter time
@@ -265,12 +267,12 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
         if decode is None:
             res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
                                 want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, None, 1.0, 0.0, False, False,
-                                d_ptr, d_bytes)
+                                d_ptr, d_bytes, seed_out)
         else:
             res = tb.fused_step(family, v, x, C.addressof(coefs), src, noise, x_next, m1, m2, order, sde_solver, out_x_next, want_x0, want_mean,
                                 want_logp, round_like_torch, out_logp, out_x0, early, has_ph, seed, off, state, decode["out"],
                                 float(decode.get("divisor", 1.0)), float(decode.get("shift", 0.0)), bool(decode.get("from_x0", False)),
-                                bool(decode.get("reciprocal", False)), d_ptr, d_bytes)
+                                bool(decode.get("reciprocal", False)), d_ptr, d_bytes, None)
         launch_count += 1 if v.shape[0] else 0
         return res
     lib = _cabi.lib()
@@ -278,7 +280,11 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
         want_logp, out_logp = False, None
     _require_cuda(v, "model_output")
     _require_cuda(x, "latents")
-    if x.dtype != torch.float32:
+    if seed_out is not None:
+        if decode is not None or x.dtype != torch.bfloat16 or not x.is_contiguous() or seed_out.dtype != torch.float32 or seed_out.shape != x.shape \
+                or not seed_out[0].is_contiguous():
+            raise ValueError("mixgrpo_b200: seed_out needs a contiguous bf16 `latents`, an fp32 view of the same shape, and no decode output")
+    elif x.dtype != torch.float32:
         x = x.to(torch.float32)
     vd = _dtype_code(v, "model_output")
     if v.shape != x.shape:
@@ -293,7 +299,7 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
                 (out_logp if out_logp is not None else torch.empty((0,), dtype=torch.float32, device=dev)) if want_logp else None,
                 f32() if want_mean else None)
     n = v[0].numel()
-    x, x_bs = _rows(x, "latents")
+    x, x_bs = (x, n) if seed_out is not None else _rows(x, "latents")
     noise_p = in_p = m1_p = m2_p = None
     in_bs = n
     keep = [v, x]
@@ -375,7 +381,12 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
         if d_out.dtype != torch.float32 or d_out.dim() != 4 or d_out.shape[0] != B or d_out[0].numel() != n or not d_out.is_contiguous():
             raise ValueError("mixgrpo_b200: decode['out'] must be a contiguous fp32 (B, C, H, W) tensor with C*H*W == elements per sample")
         xe = StepExt(d_out.data_ptr(), d_out.shape[1], d_out.shape[2], d_out.shape[3], float(decode.get("divisor", 1.0)),
-                     float(decode.get("shift", 0.0)), 1 if decode.get("from_x0", False) else 0, 1 if decode.get("reciprocal", False) else 0)
+                     float(decode.get("shift", 0.0)), 1 if decode.get("from_x0", False) else 0, 1 if decode.get("reciprocal", False) else 0,
+                     0, None, 0)
+        keep.append(xe)
+        ext = C.byref(xe)
+    elif seed_out is not None:
+        xe = StepExt(None, 0, 0, 0, 1.0, 0.0, 0, 0, 1, seed_out.data_ptr(), seed_out.stride(0) if B > 1 else n)
         keep.append(xe)
         ext = C.byref(xe)
     common_out = (out_p, out_bs, x0.data_ptr() if want_x0 else None, mean.data_ptr() if want_mean else None,
@@ -395,6 +406,16 @@ def fused_step(family: int, v: torch.Tensor, x: torch.Tensor, coefs: StepCoefs, 
     launch_count += 1
     del keep
     return (x_next if src == SRC_GIVEN else out), x0, logp, mean
+
+
+def can_seed(z: torch.Tensor, dst: torch.Tensor) -> bool:
+    """Whether ``fused_step(..., x=z, seed_out=dst)`` covers these tensors (bf16 contiguous ``z``, fp32 ``dst`` rows, the
+    256-bit vector path); otherwise seed the trajectory with ``cast_rows`` first."""
+    if z.dtype != torch.bfloat16 or not z.is_contiguous() or z.dim() < 2 or z.shape[0] == 0 or dst.dtype != torch.float32 or dst.shape != z.shape:
+        return False
+    n = z[0].numel()
+    bs = dst.stride(0) if z.shape[0] > 1 else n
+    return n % 8 == 0 and bs % 8 == 0 and dst[0].is_contiguous() and z.data_ptr() % 32 == 0 and dst.data_ptr() % 32 == 0
 
 
 def logprob_backward(family: int, v: torch.Tensor, x: torch.Tensor, x_next: torch.Tensor, grad_logp: torch.Tensor,

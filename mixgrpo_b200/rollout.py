@@ -104,7 +104,12 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
     n_steps = sigmas.size(0) - 1
     B, dev = z.shape[0], z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
-    _ops.cast_rows(z, traj[:, 0])
+    # all_latents[:, 0] = float(z) (SU:26, SU:153): written by the FIRST sampler step itself when that is a flow-family step on
+    # the vector path (it then reads the bf16 z directly), else by its own cast launch
+    first_is_flow = cfg.flow_grpo_sampling and not ("dpmsolver" in cfg.dpm_algorithm_type and cfg.dpm_apply_strategy == "all")
+    seed_in_step = (first_is_flow and (n_steps > 1 or (n_steps == 1 and decode is None)) and _ops.can_seed(z, traj[:, 0]))
+    if not seed_in_step:
+        _ops.cast_rows(z, traj[:, 0])
     acc = _ops.DeferredLogProbs(dev, n_steps, B, z[0].numel()) if (cfg.defer_log_probs and B > 0) else None
     if cfg.ode_log_probs or acc is not None:
         logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)                     # finalize also fills skipped rows with NaN
@@ -161,9 +166,11 @@ def rollout(model: Callable[[torch.Tensor, float, int], torch.Tensor], z: torch.
                 if nz is None:
                     nz = torch.randn(v.shape, device=dev, dtype=v.dtype if cfg.flow_grpo_sampling else torch.float32, generator=generator)
             lp_on = (not determistic[i]) or cfg.ode_log_probs
-            _, x0, _, _ = _ops.fused_step(fam, v, x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
+            seed0 = seed_in_step and i == 0
+            _, x0, _, _ = _ops.fused_step(fam, v, z if seed0 else x, k, src=src, noise=nz, philox=ph, sde_solver=not determistic[i], out_x_next=out,
                                           out_logp=logps_t[i] if lp_on else None, want_logp=lp_on, want_x0=keep_x0, round_like_torch=rnd,
-                                          early=early, decode=dec, defer=acc.slot(i, k) if (acc is not None and lp_on) else None)
+                                          early=early, decode=dec, defer=acc.slot(i, k) if (acc is not None and lp_on) else None,
+                                          seed_out=x if seed0 else None)
             if flash and cfg.flow_grpo_sampling:               # SU:116-117, SU:127
                 dpm_state.update(x0)
                 dpm_state.update_lower_order()

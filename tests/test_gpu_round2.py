@@ -395,3 +395,44 @@ def test_deferred_log_probs_far_samples_inactive_rows_and_graph_replay():
         rc = _cabi.lib().mixgrpo_policy_fwd(0, vd.data_ptr(), 0, xd.data_ptr(), S * 64, xnd.data_ptr(), S * 64, out[1].data_ptr(), ws.data_ptr(), ws.numel(), B,
                                             S * 64, C.byref(k), C.byref(la), _cabi.FLAG_DEFER_LOGP, torch.cuda.current_stream().cuda_stream)
         _cabi.check(rc, "policy_fwd")
+
+
+# ------------------------------------------------------------------------------------------ trajectory seed fused into step 0
+@pytest.mark.parametrize("first_sde", [False, True])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_first_step_seeds_the_trajectory(first_sde, dtype):
+    """all_latents[:, 0] = float(z) (SU:26, SU:153) written by the first sampler step itself (mixgrpo_step_ext.x_f32_out): the
+    whole rollout is bit-identical to seeding with the separate cast launch, and one launch shorter."""
+    from mixgrpo_b200 import coefs, ops, rollout as R
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_NOISE
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(31)
+    B, S, N = 4, 512, 6
+    window = [0, 1] if first_sde else [2, 3]
+    z0 = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    vs = [torch.randn(B, S, 64, device=d, generator=g).to(dtype) for _ in range(N)]
+    nz = [torch.randn(B, S, 64, device=d, generator=g).to(dtype) if i in window else None for i in range(N)]
+    det = R.window_mask(N, window)
+    sig = R.sigma_schedule(N, 3.0)
+    cfg = R.SamplerConfig(sampling_steps=N)
+    before = ops.launch_count
+    a = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, cfg, noises=nz)
+    n_fused = ops.launch_count - before
+    assert n_fused == N + 1, "N step launches + 1 finalize: no cast launch"
+    assert torch.equal(a[2][:, 0], z0.float())
+    # reference composition: cast launch + every step on the fp32 slot
+    traj = torch.empty(B, N + 1, S, 64, device=d)
+    ops.cast_rows(z0, traj[:, 0])
+    lps = torch.empty(N, B, device=d)
+    for i in range(N):
+        k, _ = coefs.flow(sig, i, cfg.eta, "ref_cuda", dtype == torch.bfloat16)
+        ops.fused_step(ops.FLOW, vs[i], traj[:, i], k, src=SRC_DETERMINISTIC if det[i] else SRC_NOISE, noise=nz[i], out_x_next=traj[:, i + 1],
+                       out_logp=lps[i], want_x0=False, round_like_torch=True)
+    assert torch.equal(a[2], traj) and torch.equal(a[3], lps.t())
+    # a float32 z (or an unaligned one) falls back to the cast launch and gives the same trajectory
+    b = R.rollout(lambda lt, s, i: vs[i], z0.float(), sig, det, cfg, noises=nz)
+    assert torch.equal(b[2], traj)
+    # the entry point refuses the seed for the stored-transition source and for non-bf16 latents
+    k, _ = coefs.flow(sig, 0, cfg.eta, "ref_cuda", dtype == torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.fused_step(ops.FLOW, vs[0], z0.float(), k, src=SRC_DETERMINISTIC, seed_out=traj[:, 0])
