@@ -405,7 +405,10 @@ def run_sample_step(
     B = z.shape[0]
     dev = z.device
     traj = torch.empty((B, n_steps + 1) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
-    _ops.cast_rows(z, traj[:, 0])
+    # all_latents[:, 0] = float(z): written by the first sampler step itself when that is a flow step on the vector path
+    first_is_flow = args.flow_grpo_sampling and not ("dpmsolver" in args.dpm_algorithm_type and args.dpm_apply_strategy == "all")
+    can_seed = first_is_flow and (n_steps > 1 or (n_steps == 1 and decode is None)) and _ops.can_seed(z, traj[:, 0])
+    seed_in_step = False                         # decided at the first iteration (progress_bar may be a tqdm: no indexing)
     logps_t = torch.empty((n_steps, B), dtype=torch.float32, device=dev)   # step-major so each kernel writes a row
     # all_log_probs is read after the loop only (SU:153-155): the step launches accumulate, ONE finalize launch writes every row
     acc = _ops.DeferredLogProbs(dev, n_steps, B, z[0].numel()) if (DEFER_LOG_PROBS and B > 0) else None
@@ -424,6 +427,10 @@ def run_sample_step(
         dec_last = {"out": decode["out"], "divisor": decode.get("divisor", 1.0), "shift": decode.get("shift", 0.0),
                     "from_x0": bool(args.drop_last_sample), "reciprocal": bool(decode.get("reciprocal", False))}
     for i in progress_bar:
+        if steps_done == 0:
+            seed_in_step = can_seed and i == 0
+            if not seed_in_step:
+                _ops.cast_rows(z, traj[:, 0])
         dec = dec_last if i == n_steps - 1 else None
         timestep_value = int(host_sig[i] * 1000)                                  # SU:63-65 without the sync
         timesteps = torch.full([encoder_hidden_states.shape[0]], timestep_value, device=dev, dtype=torch.long)
@@ -461,14 +468,17 @@ def run_sample_step(
             dpm_state.update_lower_order()
         elif args.flow_grpo_sampling:
             k, _ = _coefs.flow(sigma_schedule, i, args.eta, mode, bf16_v)
+            seed0 = seed_in_step and i == 0
             if determistic[i]:
-                _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_DETERMINISTIC, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
+                _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, z if seed0 else x, k, src=SRC_DETERMINISTIC, out_x_next=out,
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None,
+                                                          seed_out=x if seed0 else None)
             else:
                 if nz is None:
                     nz = torch.randn(pred.shape, device=dev, dtype=pred.dtype)
-                _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, x, k, src=SRC_NOISE, noise=nz, out_x_next=out,
-                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
+                _, pred_original, lp, _ = _ops.fused_step(_ops.FLOW, pred, z if seed0 else x, k, src=SRC_NOISE, noise=nz, out_x_next=out,
+                                                          out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None,
+                                                          seed_out=x if seed0 else None)
             if flash:                                                               # SU:116-117, 127
                 dpm_state.update(pred_original)
                 dpm_state.update_lower_order()
@@ -484,6 +494,8 @@ def run_sample_step(
                                                           out_x_next=out, out_logp=logps_t[i], round_like_torch=rnd, decode=dec, defer=acc.slot(i, k) if acc is not None else None)
         cur = out
         steps_done += 1
+    if steps_done == 0:
+        _ops.cast_rows(z, traj[:, 0])
     if acc is not None:
         acc.finalize(logps_t)
 
