@@ -149,9 +149,7 @@ class DeferredLogProbs:
         if buf is None:
             buf = torch.zeros(max(self.stride * self.n_launches, 8), dtype=torch.uint8, device=device)
             if not torch.cuda.is_current_stream_capturing():
-                if len(_deferred_bufs) > 64:
-                    _deferred_bufs.clear()
-                _deferred_bufs[key] = buf
+                _deferred_bufs[key] = buf            # never evicted: a captured graph may hold its address (a few KB per key)
         self.buf = buf
         self.log_scale = (C.c_float * self.n_launches)()
         self.log_norm = (C.c_float * self.n_launches)()
