@@ -115,7 +115,7 @@ typedef struct mixgrpo_step_coefs {
 } mixgrpo_step_coefs;
 
 /* Bytes of zero-initialised device workspace the step / policy kernels need for (B, n): one 32-byte record per
- * sample — a 64-bit packed accumulator ([fixed-point sum | wide-share count | arrival count], csrc/step_kernels.cu) for
+ * sample — a 64-bit packed accumulator ([fixed-point sum | wide-share count | arrival count], csrc/step_kernel.cuh) for
  * the deterministic log-prob reduction, a 32-bit epoch and a status word (csrc/policy_kernels.cu), and a 64-bit side
  * accumulator for shares too large for the packed field (csrc/step_math.cuh).  The layout does
  * not depend on B and kernels leave the accumulators zeroed again, so one allocation can be reused by successive

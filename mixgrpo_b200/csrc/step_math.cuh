@@ -1,6 +1,6 @@
 // Per-tile arithmetic of the three operator families (flow_grpo_step SU:157-210, dance_grpo_step SU:212-253, dpm_step
 // SU:273-639; SU = /root/reference/fastvideo/utils/sampling_utils.py), shared by the streaming step kernel
-// (step_kernels.cu) and the single-pass policy kernel (policy_kernels.cu).  Every product/sum the reference performs as
+// (step_kernel.cuh) and the single-pass policy kernel (policy_kernels.cu).  Every product/sum the reference performs as
 // a separate torch kernel is one __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn here (no FMA contraction), in the same order,
 // with torch's bf16 promotion roundings when RND is set.
 #pragma once

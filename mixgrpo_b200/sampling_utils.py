@@ -6,7 +6,7 @@
 
 Same names, positional/keyword signatures, return tuples, dtypes and exceptions as
 ``/root/reference/fastvideo/utils/sampling_utils.py`` (``SU``); each operator is ONE fused sm_100a
-kernel launch (csrc/step_kernels.cu) instead of ~35 eager launches and a host sync, and the log-prob
+kernel launch (csrc/step_kernel.cuh) instead of ~35 eager launches and a host sync, and the log-prob
 is differentiable w.r.t. ``model_output`` through a closed-form backward kernel
 (csrc/bwd_kernels.cu).  Additions are keyword-only: ``noise=`` (explicit noise; the reference draws it
 internally) and ``rounding=`` (see coefs.py).
