@@ -126,7 +126,10 @@ def load_ncu_traffic():
     for nm in ("r02_ode_kernel_ncu.json",):
         try:
             d = json.loads((ROOT / "profiles" / nm).read_text())
-            return d["dram_bytes_read"] + d["dram_bytes_write"], d.get("note", "")
+            l2w = [p["lts__t_sectors_srcunit_tex_op_write.sum"][0] * 32 for p in d.get("per_launch", []) if "lts__t_sectors_srcunit_tex_op_write.sum" in p]
+            note = (f"{d.get('note', '')}; per launch: DRAM read {d['dram_bytes_read']} B (= the algorithmic reads, 18.87 MB), DRAM write {d['dram_bytes_write']} B "
+                    f"(the 12.58 MB of output is still in the 126 MB L2 when the launch ends), L2-side writes {int(sum(l2w) / max(len(l2w), 1))} B (= the algorithmic writes)")
+            return d["dram_bytes_read"] + d["dram_bytes_write"], note
         except Exception:  # noqa: BLE001
             continue
     return None, "no ncu capture of this instantiation committed"
@@ -439,7 +442,7 @@ def measure_roofline(dev, peak_gbs, peak_kind):
     tot_b = sum(res[k]["bytes_per_elem"] * e * c for k, c, _ in plan)
     tot_us = sum(res[k]["us_per_launch"] * c for k, c, _ in plan)
     roof = {"bound": "hbm",
-            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 30 launches and the largest share of its device time; launched as the rollout launches it (log-prob sums accumulated, one finalize launch per 25 step launches, its time included)",
+            "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 29 launches and the largest share of its device time; launched as the rollout launches it (log-prob sums accumulated, one finalize launch per 25 step launches, its time included)",
             "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
             "unit": "GB/s", "frac": round(top["GBps"] / peak_gbs, 4), "traffic": None, "us_per_launch": top["us_per_launch"],
             "algorithmic_bytes_per_launch": e * bytes_per_elem("ode", False),
