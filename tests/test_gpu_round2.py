@@ -436,3 +436,24 @@ def test_first_step_seeds_the_trajectory(first_sde, dtype):
     k, _ = coefs.flow(sig, 0, cfg.eta, "ref_cuda", dtype == torch.bfloat16)
     with pytest.raises(ValueError):
         ops.fused_step(ops.FLOW, vs[0], z0.float(), k, src=SRC_DETERMINISTIC, seed_out=traj[:, 0])
+
+
+def test_deferred_finalize_handles_more_than_one_chunk_of_launches_and_ragged_samples():
+    """mixgrpo_logp_finalize works in chunks of 64 launches; 70 sampler steps on ragged samples (n = 5 * 63: scalar kernels, no
+    trajectory seed) must still match the self-finalizing launches bit for bit."""
+    from mixgrpo_b200 import rollout as R
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(77)
+    B, S, C, N = 3, 5, 63, 70
+    window = [10, 11, 40, 66]
+    z0 = torch.randn(B, S, C, device=d, generator=g).bfloat16()
+    vs = [torch.randn(B, S, C, device=d, generator=g) for _ in range(N)]
+    nz = [torch.randn(B, S, C, device=d, generator=g) if i in window else None for i in range(N)]
+    det = R.window_mask(N, window)
+    sig = R.sigma_schedule(N, 3.0)
+    a = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N, defer_log_probs=False), noises=nz)
+    b = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N), noises=nz)
+    assert torch.equal(a[2], b[2]) and a[3].shape == (B, N)
+    assert torch.equal(torch.nan_to_num(a[3], nan=9.0), torch.nan_to_num(b[3], nan=9.0))
+    c = R.rollout(lambda lt, s, i: vs[i], z0, sig, det, R.SamplerConfig(sampling_steps=N, ode_log_probs=False), noises=nz)
+    assert torch.equal(c[3][:, window], a[3][:, window]) and torch.isnan(c[3][:, [0, 9, 12, 65, 69]]).all()
