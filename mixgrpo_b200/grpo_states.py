@@ -37,16 +37,16 @@ class GRPOTrainingStates:
     exp_decay_k: float = 0.1
 
     def __post_init__(self):
-        if self.sample_strategy == "decay":                       # grpo_states.py:48-52
-            if self.max_iters_per_group is None:
-                self.max_iters_per_group = self.iters_per_group
-            if self.min_iters_per_group is None:
-                self.min_iters_per_group = max(1, self.iters_per_group // 4)
-        self.init_timestep = self.cur_timestep
+        self.init_timestep = self.cur_timestep                    # where roll_back_start() returns to
+        if self.sample_strategy == "decay":                       # defaults of the decaying budget (grpo_states.py:48-52)
+            hi, lo = self.max_iters_per_group, self.min_iters_per_group
+            self.max_iters_per_group = self.iters_per_group if hi is None else hi
+            self.min_iters_per_group = max(1, self.iters_per_group // 4) if lo is None else lo
 
     def set_params(self, params: dict):
-        for name, value in params.items():
-            setattr(self, name, value)
+        """Overwrite any attributes by name (the reference's resume hook)."""
+        for name in params:
+            setattr(self, name, params[name])
 
     # ---- per-window iteration budget -------------------------------------------------------
     def get_dynamic_iters_per_group(self) -> int:
@@ -99,6 +99,5 @@ class GRPOTrainingStates:
         return list(range(self.cur_timestep, min(self.cur_timestep + self.group_size, self.max_timesteps)))
 
     def is_training_complete(self) -> bool:
-        if self.sample_strategy in ["progressive", "decay"]:
-            return self.cur_timestep >= self.max_timesteps
-        return False
+        """Only the two strategies that walk the schedule once ever finish (grpo_states.py:150-159)."""
+        return self.sample_strategy in ("progressive", "decay") and self.cur_timestep >= self.max_timesteps
