@@ -5,9 +5,12 @@
     ncu --set full --clock-control none --import-source on -o gpurun_out/r02_targets python tools/ncu_targets.py
     python tools/ncu_full_summary.py gpurun_out/r02_targets.ncu-rep --kernel-regex '<regex>' --json profiles/<name>.json ...
 
-Launch order (3 launches each, rotating buffer sets so no input is hot in L2 beyond what ncu's cache control leaves):
+Launch order (3 launches each, rotating buffer sets so no input is hot in L2 beyond what ncu's cache control leaves); the
+rollout's step launches are issued as the rollout issues them — log-prob sums accumulated (MIXGRPO_FLAG_DEFER_LOGP), ONE finalize:
+  0. first step: bf16 latent in, all_latents[:, 0] and [:, 1] out   mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0,EXT=2>   (1 launch per step)
   1. Euler-ODE sampler step + log-prob        mg::step_kernel<flow,bf16,SRC_DETERMINISTIC,OUT=0>   (21 of a step's 29 launches)
-  2. SDE sampler step + log-prob, no x0       mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0>           (4 launches)
+  2. SDE sampler step + log-prob, no x0       mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0>           (3 launches)
+  2b. mg::logp_finalize_kernel                                                                   (1 launch)
   3. window forward, 4 items in one launch    mg::policy_fwd_multi_kernel<flow,bf16>               (1 launch)
   4. window backward, 4 items in one launch   mg::policy_bwd_multi_kernel<flow,bf16>               (1 launch)
   5. stored-transition log-prob (SRC_GIVEN)   mg::step_kernel<flow,bf16,SRC_GIVEN,OUT=0>           (drop-in / per-step path)
@@ -43,10 +46,16 @@ def main():
     sig = (3.0 * sig) / (1 + 2.0 * sig)
     k, _ = coefs.flow(sig, 9, 0.7, "ref_cuda", True)
     ks = [coefs.flow(sig, t, 0.7, "ref_cuda", True)[0] for t in range(J)]
+    acc = ops.DeferredLogProbs(dev, 7, B, S * C)
+    z0 = torch.randn(B, S, C, device=dev, generator=g).bfloat16()
+    seed_slot = torch.empty(B, S, C, device=dev)
+    ops.fused_step(ops.FLOW, vs[7], z0, k, src=SRC_NOISE, noise=es[7], out_x_next=outs[7], want_x0=False, round_like_torch=True, early=1, defer=acc.slot(6, k),
+                   seed_out=seed_slot)
     for i in range(3):
-        ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], out_logp=lps[i], want_x0=False, round_like_torch=True, early=1)
+        ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_DETERMINISTIC, out_x_next=outs[i], want_x0=False, round_like_torch=True, early=1, defer=acc.slot(i, k))
     for i in range(3, 6):
-        ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], out_logp=lps[i], want_x0=False, round_like_torch=True, early=1)
+        ops.fused_step(ops.FLOW, vs[i], xs[i], k, src=SRC_NOISE, noise=es[i], out_x_next=outs[i], want_x0=False, round_like_torch=True, early=1, defer=acc.slot(i, k))
+    acc.finalize(torch.empty(7, B, device=dev))
     for q in range(2):
         idx = [q * J + j for j in range(J)]
         ops.policy_forward_multi(ops.FLOW, [vs[i] for i in idx], [xs[i] for i in idx], [outs[(i + 1) % NS] for i in idx], ks, [old[i] for i in idx], adv,
