@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MIXGRPO_ABI_VERSION 5
+#define MIXGRPO_ABI_VERSION 6
 
 /* element type of model_output / noise / grad_model_output */
 enum { MIXGRPO_F32 = 0, MIXGRPO_BF16 = 1 };
@@ -68,12 +68,14 @@ typedef struct mixgrpo_philox_args {
                                             are loaded before the wait */
 
 #define MIXGRPO_FLAG_DEFER_LOGP       8u /* step kernels: accumulate the launch's per-sample log-prob sums into `workspace` — then the
-                                            CALLER's own B records for THIS launch, mixgrpo_step_workspace_bytes(B, n) bytes, zeroed —
+                                            CALLER's own records for THIS launch, mixgrpo_deferred_workspace_bytes(B, n) bytes, zeroed —
                                             with a fire-and-forget reduction and do not finalize; logp_out may be NULL.  A rollout's
                                             log-probs are only read after the rollout (SU:153-155), so its 25 step launches skip the
                                             returning atomic that otherwise keeps every CTA resident for an L2 round trip (0.7 us of a
-                                            7 us launch at (12,4096,64)); ONE mixgrpo_logp_finalize launch then turns all records into
-                                            log-probs.  Same packed integer sums, hence the same bits as the immediate path. */
+                                            7 us launch at (12,4096,64)), and — nobody having to see the last arrival — run as
+                                            128-thread CTAs of one half-tile each whose reductions are spread over 8 sub-records per
+                                            sample (another 0.45 us); ONE mixgrpo_logp_finalize launch then turns all records into
+                                            log-probs.  Same per-half-tile integer sums, hence the same bits as the immediate path. */
 
 /* error codes */
 #define MIXGRPO_EINVAL   (-1)  /* bad argument (null pointer, bad enum, B<=0, n<=0) */
@@ -122,12 +124,21 @@ typedef struct mixgrpo_step_coefs {
  * launches of any batch size on the same stream (never by launches that may run concurrently). */
 int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t n);
 
+/* Bytes of zero-initialised device workspace ONE launch with MIXGRPO_FLAG_DEFER_LOGP needs for (B, n): eight such 32-byte
+ * records per sample (256 B), over which the launch spreads the sample's arrivals so that its thousands of fire-and-forget
+ * reductions do not serialise on 12 addresses in the L2.  mixgrpo_logp_finalize adds them up (integers: exact) and leaves them
+ * zeroed.  A rollout of N step launches holds N such blocks, launch_stride_bytes apart. */
+int64_t mixgrpo_deferred_workspace_bytes(int64_t B, int64_t n);
+
 /* ABI / build introspection. */
 int mixgrpo_abi_version(void);
 const char* mixgrpo_build_info(void);          /* e.g. "sm_100a nvcc 12.9 ..." (static string) */
 int mixgrpo_set_tuning(int key, int value);    /* knobs (0: max CTAs/sample, 1: PDL on/off, 2: peer-wait timeout in ms, 0 = forever,
                                                   3: single-pass policy kernel CTAs/SM, 4: its cooperative launch on/off, 5: its wait
-                                                  timeout in ms); returns the previous value or <0 */
+                                                  timeout in ms, 6: deferred step launches as 128-thread CTAs — 0 never, 1 when the grid exceeds one
+                                                  wave (default), 2 always, 7: CTA size of the log-prob backward kernels (128 | 256), 8: read-only count of
+                                                  step launches issued in the 128-thread shape); returns the
+                                                  previous value or <0 */
 const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGetErrorString for >0) */
 
 /* ---- fused sampler step + Gaussian transition log-prob ---------------------------------------
@@ -193,7 +204,8 @@ int mixgrpo_dpm_step(const void* v, int v_dtype, const float* x, int64_t x_bs,
                      int src, unsigned flags, void* stream, const mixgrpo_step_ext* ext);
 
 /* Finalizes the log-probs of `n_launches` step launches issued with MIXGRPO_FLAG_DEFER_LOGP (stream-ordered after them; ONE
- * launch): launch i accumulated into the B records at workspace + i * launch_stride_bytes;
+ * launch): launch i accumulated into the records at workspace + i * launch_stride_bytes (launch_stride_bytes >=
+ * mixgrpo_deferred_workspace_bytes(B, n), a multiple of 8);
  *   logp_out[i * out_stride + b] = -mean(d^2 / 2 s^2) - log_scale_host[i] - log_norm_host[i]      (SU:201-208)
  * with the per-step scalars of that launch's mixgrpo_step_coefs.  active_host[i] == 0 (nullable = all active): launch i did not
  * accumulate (e.g. a deterministic step whose log-prob was skipped) — its row is filled with NaN.  Records are left zeroed.

@@ -21,7 +21,7 @@ POLICY_MAX_ITEMS = 8
 ADV_GROUP_LOCAL, ADV_GROUP_SPLIT, ADV_GLOBAL = 0, 1, 2
 EUNSUPPORTED = -4
 PEER_MAX_WORLD, PEER_HANDLE_BYTES = 16, 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class StepCoefs(C.Structure):
@@ -64,6 +64,7 @@ _IP = C.POINTER(PolicyItem)
 # name -> (restype, argtypes); every symbol include/mixgrpo_b200.h declares
 SIGNATURES = {
     "mixgrpo_step_workspace_bytes": (_I64, [_I64, _I64]),
+    "mixgrpo_deferred_workspace_bytes": (_I64, [_I64, _I64]),
     "mixgrpo_abi_version": (_I, []),
     "mixgrpo_build_info": (C.c_char_p, []),
     "mixgrpo_set_tuning": (_I, [_I, _I]),

@@ -30,7 +30,7 @@ template <int FAM, class VT, bool RND, int VEC, bool EARLY>
 __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_constant__ BwdParams p) {
   if constexpr (!EARLY) pdl_prologue();
   const int b = blockIdx.y;
-  const long long idx = ((long long)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;        // blockDim.x = g_bwd_threads (128 | 256)
   const bool active = idx < p.n;
   const float* c = p.k.c;
   float v[VEC], x[VEC], xn[VEC], t[VEC], mu[VEC], x0[VEC], g[VEC];
@@ -112,13 +112,14 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
 
 template <int FAM, class VT, bool RND>
 static int launch_bwd(const BwdParams& p, int64_t B, bool vec, bool early, cudaStream_t st) {
+  const int thr = g_bwd_threads;
   if (vec) {
-    dim3 grid((unsigned)((p.n + (long long)kThreads * kVec - 1) / ((long long)kThreads * kVec)), (unsigned)B);
-    if (early) launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, true>, grid, kThreads, 0, st, p);
-    else launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, false>, grid, kThreads, 0, st, p);
+    dim3 grid((unsigned)((p.n + (long long)thr * kVec - 1) / ((long long)thr * kVec)), (unsigned)B);
+    if (early) launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, true>, grid, thr, 0, st, p);
+    else launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, false>, grid, thr, 0, st, p);
   } else {
-    dim3 grid((unsigned)((p.n + kThreads - 1) / kThreads), (unsigned)B);
-    launch_pdl(logprob_bwd_kernel<FAM, VT, RND, 1, false>, grid, kThreads, 0, st, p);
+    dim3 grid((unsigned)((p.n + thr - 1) / thr), (unsigned)B);
+    launch_pdl(logprob_bwd_kernel<FAM, VT, RND, 1, false>, grid, thr, 0, st, p);
   }
   return (int)cudaGetLastError();
 }

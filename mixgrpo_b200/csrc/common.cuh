@@ -125,6 +125,7 @@ __device__ __forceinline__ void philox_normal4(unsigned long long q, unsigned lo
 // cuBLAS) the attribute is inert and ordering is the ordinary stream order.  Measured: -0.4 us per chained launch,
 // -1.1 us with early loads (profiles/r01_design_space.md).
 extern int g_use_pdl;   // mixgrpo_set_tuning key 1 (bench A/B knob), defined in step_flow.cu
+extern int g_bwd_threads;   // key 7: threads per CTA of the log-prob backward kernels (128 | 256), defined in step_flow.cu
 }  // namespace mg
 int mixgrpo_peer_set_timeout_ms(int ms);   // mixgrpo_set_tuning key 2, defined in peer_kernels.cu
 int mixgrpo_policy_set_tuning(int key, int value);   // keys 3-5, defined in policy_kernels.cu
@@ -151,15 +152,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// second stage of the CTA reduction: lanes 0..7 hold the 8 warp sums, the other lanes exact zeros — the xor-16 and xor-8
-// levels of warp_sum would only add those zeros, so three levels give the same bits
-static_assert(kThreads / 32 == 8, "warp_sum8 assumes 8 warps per CTA");
-__device__ __forceinline__ float warp_sum8(float v) {
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // ---------------------------------------------------------------- clipped-ratio GRPO loss, one sample
 // TR:560-583 for ONE log-prob (TR = fastvideo/train_grpo_flux.py).  Shared by the batch loss kernel and by the
 // fused policy path, where the forward log-prob kernel's finalizer and every CTA of the backward kernel

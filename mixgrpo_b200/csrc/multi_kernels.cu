@@ -63,15 +63,12 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   if (lane == 0) s_warp[warp] = acc;
   __syncthreads();
   if (warp != 0) return;
-  float t = lane < kThreads / 32 ? s_warp[lane] : 0.f;
-  t = warp_sum8(t);
+  unsigned long long* rec = p.acc + kWsStride * (long long)blockIdx.y;
+  const unsigned long long add = cta_share(s_warp, lane, __fmul_rn((float)n, q.k.two_var), 2 * (int)gridDim.x, rec);   // step_math.cuh
   if (lane == 0) {
     const int ctas = gridDim.x;
-    const float r = __fdiv_rn(t, __fmul_rn((float)n, q.k.two_var));
-    unsigned long long* rec = p.acc + kWsStride * (long long)blockIdx.y;
-    const unsigned long long add = packed_share(r, ctas, rec);
     const unsigned long long old = atomicAdd(rec, add);
-    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
+    if ((old & kArrivalMask) == (unsigned long long)(ctas - 1)) {
       const float s = packed_total(old + add, rec);
       const float lp = __fsub_rn(__fsub_rn(-s, q.k.log_scale), q.k.log_norm);        // SU:201-208
       q.logp[b] = lp;
@@ -95,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) policy_bwd_multi_kernel(const __grid
   if (p.early == 0) pdl_prologue();
   const int item = blockIdx.y / p.B, b = blockIdx.y - item * p.B;
   const MultiItem& q = p.it[item];
-  const long long idx = ((long long)blockIdx.x * kThreads + threadIdx.x) * kVec;
+  const long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kVec;       // blockDim.x = g_bwd_threads (128 | 256)
   const bool active = idx < p.n;
   const float* c = q.k.c;
   float v[kVec], x[kVec], xn[kVec], t[kVec], g[kVec];
@@ -224,15 +221,16 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_bwd_multi(i
   p.early = (flags & MIXGRPO_FLAG_PDL_EARLY_LOADS) ? 2 : 0;
   const bool rnd = (flags & MIXGRPO_FLAG_ROUND_LIKE_TORCH) != 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((unsigned)((n + (long long)kThreads * kVec - 1) / ((long long)kThreads * kVec)), (unsigned)(B * n_items));
+  const int thr = g_bwd_threads;
+  dim3 grid((unsigned)((n + (long long)thr * kVec - 1) / ((long long)thr * kVec)), (unsigned)(B * n_items));
   if (family == kFlow) {
-    if (v_dtype == MIXGRPO_F32) launch_pdl(policy_bwd_multi_kernel<kFlow, float, false>, grid, kThreads, 0, st, p);
-    else if (rnd) launch_pdl(policy_bwd_multi_kernel<kFlow, __nv_bfloat16, true>, grid, kThreads, 0, st, p);
-    else launch_pdl(policy_bwd_multi_kernel<kFlow, __nv_bfloat16, false>, grid, kThreads, 0, st, p);
+    if (v_dtype == MIXGRPO_F32) launch_pdl(policy_bwd_multi_kernel<kFlow, float, false>, grid, thr, 0, st, p);
+    else if (rnd) launch_pdl(policy_bwd_multi_kernel<kFlow, __nv_bfloat16, true>, grid, thr, 0, st, p);
+    else launch_pdl(policy_bwd_multi_kernel<kFlow, __nv_bfloat16, false>, grid, thr, 0, st, p);
   } else {
-    if (v_dtype == MIXGRPO_F32) launch_pdl(policy_bwd_multi_kernel<kDance, float, false>, grid, kThreads, 0, st, p);
-    else if (rnd) launch_pdl(policy_bwd_multi_kernel<kDance, __nv_bfloat16, true>, grid, kThreads, 0, st, p);
-    else launch_pdl(policy_bwd_multi_kernel<kDance, __nv_bfloat16, false>, grid, kThreads, 0, st, p);
+    if (v_dtype == MIXGRPO_F32) launch_pdl(policy_bwd_multi_kernel<kDance, float, false>, grid, thr, 0, st, p);
+    else if (rnd) launch_pdl(policy_bwd_multi_kernel<kDance, __nv_bfloat16, true>, grid, thr, 0, st, p);
+    else launch_pdl(policy_bwd_multi_kernel<kDance, __nv_bfloat16, false>, grid, thr, 0, st, p);
   }
   return (int)cudaGetLastError();
 }

@@ -151,13 +151,11 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   if (tid < K) {
     my_b = (t_lo + tid) / p.tps;
     const float* w = s_part + tid * (kThreads / 32);
-    // the order of mg::step_kernel's second-stage xor-shuffle tree over the 8 warp sums
-    const float t = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[4]), __fadd_rn(w[2], w[6])), __fadd_rn(__fadd_rn(w[1], w[5]), __fadd_rn(w[3], w[7])));
-    const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
     unsigned long long* rec = p.acc + kWsStride * my_b;
-    const unsigned long long add = packed_share(r, p.tps, rec);
+    // mg::step_kernel's arithmetic: each half-tile's four warp sums in its xor-shuffle order, fixed point per half (step_math.cuh)
+    const unsigned long long add = cta_share_serial(w, __fmul_rn((float)n, p.k.two_var), 2 * p.tps, rec);
     const unsigned long long old = atomicAdd(rec, add);
-    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(p.tps - 1)) {
+    if ((old & kArrivalMask) == (unsigned long long)(p.tps - 1)) {
       const float q = packed_total(old + add, rec);
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);      // SU:201-208
       p.logp_out[my_b] = lp;

@@ -4,6 +4,19 @@
 namespace mg {
 int g_max_ctas_per_sample = kMaxCtasPerSample;          // bench knob (mixgrpo_set_tuning key 0)
 int g_use_pdl = 1;                                      // bench knob (key 1): programmatic dependent launch on/off
+int g_bwd_threads = kThreads;                           // knob (key 7): CTA size of the log-prob backward kernels
+int g_half_ctas = 1;                                    // knob (key 6): deferred launches in the 128-thread shape (0 never, 1 auto, 2 always)
+long long g_half_launches = 0;
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
 int policy_fwd_dance(StepParams& p, int v_dtype, int64_t B, bool vec, bool rnd, cudaStream_t st);   // step_dance.cu
 }  // namespace mg
 
@@ -17,13 +30,27 @@ extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_step_workspace
   return ((B * (int64_t)(kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
 }
 
+extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_deferred_workspace_bytes(int64_t B, int64_t n) {
+  if (B <= 0 || n <= 0) return 0;
+  // kDeferSubs records per sample: a deferred launch spreads the sample's arrivals over them (step_math.cuh)
+  return ((B * (int64_t)(kDeferSubs * kWsStride * sizeof(unsigned long long)) + 255) / 256) * 256;
+}
+
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
   if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
   if (key >= 3 && key <= 5) return mixgrpo_policy_set_tuning(key, value);
-  if (key == 1) {
-    if (value != 0 && value != 1) return MIXGRPO_EINVAL;
-    const int old = g_use_pdl;
-    g_use_pdl = value;
+  if (key == 8) return (int)(g_half_launches & 0x7fffffff);       // read-only: launches issued in the 128-thread shape
+  if (key == 7) {
+    if (value != kThreads && value != kHalfThreads) return MIXGRPO_EINVAL;
+    const int old = g_bwd_threads;
+    g_bwd_threads = value;
+    return old;
+  }
+  if (key == 1 || key == 6) {
+    if (value < 0 || value > (key == 6 ? 2 : 1)) return MIXGRPO_EINVAL;
+    int& knob = key == 1 ? g_use_pdl : g_half_ctas;
+    const int old = knob;
+    knob = value;
     return old;
   }
   if (key != 0 || value < 1 || value > kMaxCtasPerSample) return MIXGRPO_EINVAL;
@@ -95,18 +122,40 @@ struct FinalizeParams {
   unsigned long long active;                      // bit i: launch i accumulated
 };
 
-// one thread per (launch, sample) record: fold the side words in, write the log-prob, leave the record zeroed
+// kDeferSubs lanes per (launch, sample): each takes one sub-record (accumulator + side words), the group adds them up as integers,
+// its first lane writes the log-prob; every word is left zeroed
 __global__ void __launch_bounds__(128) logp_finalize_kernel(const __grid_constant__ FinalizeParams p) {
   pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.n_launches * p.B) return;
-  const int i = idx / p.B, b = idx - i * p.B;
-  unsigned long long* rec = p.ws + (long long)i * p.stride_words + kWsStride * b;
-  float lp = __int_as_float(0x7fc00000);
-  if ((p.active >> i) & 1ull) {
-    const float q = packed_total(*rec, rec);
-    lp = __fsub_rn(__fsub_rn(-q, p.log_scale[i]), p.log_norm[i]);                 // SU:201-208
+  const int r = idx / kDeferSubs, sub = idx - r * kDeferSubs;
+  const bool live = r < p.n_launches * p.B;
+  const int i = live ? r / p.B : 0, b = live ? r - i * p.B : 0;
+  const bool active = live && ((p.active >> i) & 1ull);
+  unsigned long long tot = 0ull, wide = 0ull, huge = 0ull;
+  if (active) {
+    unsigned long long* rec = p.ws + (long long)i * p.stride_words + ((long long)kDeferSubs * b + sub) * kWsStride;
+    tot = *rec;
     *rec = 0ull;
+    if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) {       // some part of this sub-record went to the side words
+      wide = atomicExch(rec + kWsWide, 0ull);
+      huge = atomicExch(rec + kWsHuge, 0ull);
+    }
+  }
+  unsigned long long bad = wide >> 63;
+  wide &= ~(1ull << 63);
+#pragma unroll
+  for (int o = kDeferSubs / 2; o > 0; o >>= 1) {                   // groups of kDeferSubs lanes are aligned inside the warp
+    tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    wide += __shfl_xor_sync(0xffffffffu, wide, o);
+    huge += __shfl_xor_sync(0xffffffffu, huge, o);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (!live || sub != 0) return;
+  float lp = __int_as_float(0x7fc00000);
+  if (active && !bad) {
+    double q = (double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0);
+    q += (double)wide * (1.0 / 16777216.0) + (double)huge;                        // packed_total's association (adds +0.0 when nothing went wide)
+    lp = __fsub_rn(__fsub_rn(-(float)q, p.log_scale[i]), p.log_norm[i]);          // SU:201-208
   }
   p.out[(long long)i * p.out_stride + b] = lp;
 }
@@ -121,7 +170,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_logp_finalize(void
                                                                             const float* log_scale_host, const float* log_norm_host,
                                                                             const int* active_host, float* logp_out, int64_t out_stride, void* stream) {
   if (!workspace || !logp_out || !log_scale_host || !log_norm_host || n_launches <= 0 || n_launches > 4096 || B <= 0 || B > 65535 ||
-      launch_stride_bytes < B * (int64_t)(kWsStride * sizeof(unsigned long long)) || (launch_stride_bytes % 8) != 0 || out_stride < B ||
+      launch_stride_bytes < B * (int64_t)(kDeferSubs * kWsStride * sizeof(unsigned long long)) || (launch_stride_bytes % 8) != 0 || out_stride < B ||
       (reinterpret_cast<uintptr_t>(workspace) % 8) != 0)
     return MIXGRPO_EINVAL;
   for (int64_t lo = 0; lo < n_launches; lo += kFinalizeChunk) {
@@ -138,7 +187,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_logp_finalize(void
       p.log_norm[i] = log_norm_host[lo + i];
       if (!active_host || active_host[lo + i]) p.active |= 1ull << i;
     }
-    const int total = p.n_launches * p.B;
+    const int total = p.n_launches * p.B * kDeferSubs;
     launch_pdl(logp_finalize_kernel, (total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream), p);
     const int rc = (int)cudaGetLastError();
     if (rc != 0) return rc;

@@ -13,9 +13,9 @@
 // same bf16 rounding points when MIXGRPO_FLAG_ROUND_LIKE_TORCH is set, so x_next / x0 / mean are
 // bit-identical to the reference on identical inputs.  Only the log-prob reduction order differs.
 //
-// log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> CTA -> ONE packed fixed-point atomicAdd per
+// log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> half-tile (4 warps) -> fixed point -> ONE packed atomicAdd per
 // CTA (count + sum in a 64-bit word): order-independent, hence bitwise reproducible; the last arriver
-// writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below.
+// writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below and in step_math.cuh.
 #pragma once
 #include "step_math.cuh"
 
@@ -35,6 +35,7 @@ struct StepParams {
   unsigned long long* acc;
   long long n, x_bs, in_bs, out_bs;
   int B, tiles;
+  int parts;                // half-tiles per sample of the 256-thread tiling = 2 x (256-thread CTAs per sample): the cap of packed_part
   mixgrpo_step_coefs k;
   unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
   const unsigned long long* philox_state;          // SRC_PHILOX, graph-safe: device {seed, base offset} (or nullptr)
@@ -120,9 +121,15 @@ __device__ __forceinline__ void store_tile(float* base, long long off, long long
 // EXT (compile time): 0 none; 1 also emit the decode-ready tensor; 2 trajectory seed (x read as bf16, its fp32 widening stored
 // too) — mixgrpo_step_ext; their own instantiations, so the other steps of a
 // rollout that do not need it keep their register budget
-template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, int EXT>
-__global__ void __launch_bounds__(kThreads, ((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE) || EXT == 1 || SRC == MIXGRPO_SRC_PHILOX) ? 4 : 6)
+// HALF (compile time): the deferred rollout launches' shape — 128-thread CTAs, one half-tile (1024 scalars) each, twice as many of
+// them per SM, no finalization code: finer-grained CTA turnover and one fire-and-forget reduction into one of the sample's
+// kDeferSubs sub-records.  Measured on the Euler-ODE step at (12,4096,64): -0.45 us of 6.15 (profiles/r02_design_space.md §4).
+template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, bool VECTOR, int OUT, int EXT, bool HALF>
+__global__ void __launch_bounds__(HALF ? kHalfThreads : kThreads,
+                                  (((FAM == kDpm && ORDER >= 2) || OUT == 2 || !VECTOR || (FAM == kDance && SDE) || EXT == 1 || SRC == MIXGRPO_SRC_PHILOX) ? 4 : 6) * (HALF ? 2 : 1))
 step_kernel(const __grid_constant__ StepParams p) {
+  static_assert(!HALF || VECTOR, "the 128-thread shape is vector-only");
+  constexpr int TILE = HALF ? kHalfTile : kTile;
   // Programmatic dependent launch: inputs the immediately preceding launch cannot have written are requested BEFORE
   // griddepcontrol.wait, so their DRAM latency overlaps that launch's drain (MIXGRPO_FLAG_PDL_EARLY_V / _EARLY_LOADS)
   // (the host only sets p.early when every CTA owns exactly one tile, so "first iteration" is the only iteration)
@@ -134,7 +141,7 @@ step_kernel(const __grid_constant__ StepParams p) {
   float acc = 0.f;
 
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-    const long long off = (long long)tile * kTile;
+    const long long off = (long long)tile * TILE;
     // vector path: n % 8 == 0, so a thread's 8 scalars are all inside or all outside the sample
     if (VECTOR && off + threadIdx.x * kVec >= n) continue;
     float v[kVec], x[kVec], a[kVec], m1[kVec], m2[kVec];
@@ -199,19 +206,25 @@ step_kernel(const __grid_constant__ StepParams p) {
   }
   if (p.logp_out == nullptr && !p.defer) return;
 
-  __shared__ float s_warp[kThreads / 32];
+  __shared__ float s_warp[(HALF ? kHalfThreads : kThreads) / 32];
   acc = warp_sum(acc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) s_warp[warp] = acc;
   __syncthreads();
-  if (warp != 0) return;                           // warps 1..7 are done: nothing waits on the atomic
-  float t = lane < kThreads / 32 ? s_warp[lane] : 0.f;
-  t = warp_sum8(t);
+  if (warp != 0) return;                           // the other warps are done: nothing waits on the atomic
+  const float denom = __fmul_rn((float)n, p.k.two_var);
+  // a deferred launch spreads a sample's arrivals over kDeferSubs records; side words of the same sub-record
+  unsigned long long* rec = p.defer ? p.acc + ((long long)kDeferSubs * b + (blockIdx.x & (kDeferSubs - 1))) * kWsStride : p.acc + kWsStride * b;
+  if constexpr (HALF) {
+    const float t = half_sum(s_warp, lane);
+    if (lane == 0) {
+      const unsigned long long add = packed_part(__fdiv_rn(t, denom), p.parts, rec) + 1ull;
+      asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(rec), "l"(add) : "memory");
+    }
+  } else {
+  const unsigned long long add = cta_share(s_warp, lane, denom, p.parts, rec);
   if (lane == 0) {
     const int ctas = gridDim.x;
-    const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
-    unsigned long long* rec = p.acc + kWsStride * b;
-    const unsigned long long add = packed_share(r, ctas, rec);
     if (p.defer) {
       // a true reduction (REDG.E.ADD.64): nothing comes back, so the CTA retires without an L2 round trip; the sums are
       // turned into log-probs by mixgrpo_logp_finalize after the rollout.  Spelled in PTX: nvcc keeps an ATOMG otherwise.
@@ -219,7 +232,7 @@ step_kernel(const __grid_constant__ StepParams p) {
       return;
     }
     const unsigned long long old = atomicAdd(rec, add);
-    if ((old & (unsigned long long)kMaxCtasPerSample) == (unsigned long long)(ctas - 1)) {
+    if ((old & kArrivalMask) == (unsigned long long)(ctas - 1)) {
       const float q = packed_total(old + add, rec);
       // mean_i[ -(d_i^2)/(2 s^2) - log s - log sqrt(2 pi) ]   (SU:201-208)
       const float lp = __fsub_rn(__fsub_rn(-q, p.k.log_scale), p.k.log_norm);
@@ -240,10 +253,15 @@ step_kernel(const __grid_constant__ StepParams p) {
       }
     }
   }
+  }  // !HALF
 }
 
 // ------------------------------------------------------------------ host-side dispatch
 extern int g_max_ctas_per_sample;                       // bench knob (mixgrpo_set_tuning key 0), defined in step_flow.cu
+extern int g_half_ctas;                                 // knob (key 6): deferred launches use the 128-thread shape — 0 never, 1 when the
+                                                        // 256-thread grid exceeds one wave (default), 2 always
+int sm_count();                                         // SMs of the current device (cached), step_flow.cu
+extern long long g_half_launches;                       // launches issued in the 128-thread shape so far (key 8 reads it)
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -251,9 +269,22 @@ template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, b
 static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
+  p.parts = 2 * ctas;
+  if constexpr (VECTOR) {
+    // a rollout's deferred launches: one 128-thread CTA per half-tile (never looping, so the parts are the same half-tiles) —
+    // when the 256-thread grid is more than one wave of 6 CTAs per SM.  Measured (B200): (12,4096,64) 1536 CTAs -0.2 us of 6.15,
+    // (24,4096,64) -4 % on the whole step; a sub-wave grid, (24,1024,64) = 768 CTAs, is 0.25 us SLOWER with twice the CTAs to dispatch
+    if (p.defer && ctas == p.tiles && (g_half_ctas == 2 || (g_half_ctas == 1 && (long long)ctas * p.B > 6LL * sm_count()))) {
+      p.tiles = (int)((p.n + kHalfTile - 1) / kHalfTile);
+      ++g_half_launches;
+      dim3 grid((unsigned)p.tiles, (unsigned)p.B);
+      launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, EXT, true>, grid, kHalfThreads, 0, st, p);
+      return (int)cudaGetLastError();
+    }
+  }
   if (ctas != p.tiles || !VECTOR) p.early = 0;           // early loads assume one tile per CTA (no loop-carried state in the kernel)
   dim3 grid((unsigned)ctas, (unsigned)p.B);
-  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT, EXT>, grid, kThreads, 0, st, p);
+  launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, VECTOR, OUT, EXT, false>, grid, kThreads, 0, st, p);
   return (int)cudaGetLastError();
 }
 
@@ -306,7 +337,7 @@ static inline bool check_common(const void* v, const float* x, int64_t B, int64_
     *err = MIXGRPO_EINVAL;
     return false;
   }
-  if ((logp || defer) && (!ws || ws_bytes < mixgrpo_step_workspace_bytes(B, n))) {
+  if ((logp || defer) && (!ws || ws_bytes < (defer ? mixgrpo_deferred_workspace_bytes(B, n) : mixgrpo_step_workspace_bytes(B, n)))) {
     *err = ws ? MIXGRPO_ENOSPACE : MIXGRPO_EINVAL;
     return false;
   }
@@ -320,7 +351,7 @@ static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_
   p.x_out = x_out; p.x0_out = x0_out; p.mean_out = mean_out; p.logp_out = logp_out;
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
-  p.B = (int)B; p.tiles = 0; p.k = *k;
+  p.B = (int)B; p.tiles = 0; p.parts = 0; p.k = *k;
   p.philox_seed = p.philox_offset = 0ull;
   p.philox_state = nullptr;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};

@@ -142,14 +142,14 @@ class DeferredLogProbs:
 
     def __init__(self, device: torch.device, n_launches: int, B: int, n: int):
         self.device, self.n_launches, self.B = device, int(n_launches), int(B)
-        self.stride = int(_cabi.lib().mixgrpo_step_workspace_bytes(B, n))
+        self.stride = int(_cabi.lib().mixgrpo_deferred_workspace_bytes(B, n))     # 8 spread sub-records per sample
         st = _stream_ptr(device)
         key = (device.index if device.index is not None else torch.cuda.current_device(), st, self.stride * self.n_launches)
         buf = _deferred_bufs.get(key)
         if buf is None:
             buf = torch.zeros(max(self.stride * self.n_launches, 8), dtype=torch.uint8, device=device)
             if not torch.cuda.is_current_stream_capturing():
-                _deferred_bufs[key] = buf            # never evicted: a captured graph may hold its address (a few KB per key)
+                _deferred_bufs[key] = buf            # never evicted: a captured graph may hold its address (77 KB per key for a 25-step rollout of 12 samples)
         self.buf = buf
         self.log_scale = (C.c_float * self.n_launches)()
         self.log_norm = (C.c_float * self.n_launches)()

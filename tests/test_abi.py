@@ -57,6 +57,10 @@ def test_host_side_argument_validation_needs_no_gpu():
     assert lib.mixgrpo_step_workspace_bytes(12, 4096 * 64) == 512
     assert lib.mixgrpo_step_workspace_bytes(0, 10) == 0
     assert lib.mixgrpo_step_workspace_bytes(100, 10) == 3328
+    # a deferred launch spreads a sample's arrivals over 8 such records
+    assert lib.mixgrpo_deferred_workspace_bytes(12, 4096 * 64) == 12 * 256
+    assert lib.mixgrpo_deferred_workspace_bytes(0, 10) == 0
+    assert lib.mixgrpo_deferred_workspace_bytes(3, 10) == 768
     # null pointers / bad sizes / bad enums are rejected with MIXGRPO_EINVAL before any launch
     assert lib.mixgrpo_flow_step(None, 1, None, 0, None, None, 0, None, 0, None, None, None, None, 0, 1, 8, ctypes.byref(k), 0, 0, None, None) == -1
     assert lib.mixgrpo_dpm_step(1, 1, 1, 8, None, None, None, 4, None, 8, None, None, None, None, 0, 1, 8, ctypes.byref(k), 2, 0, None, None) == -1

@@ -397,6 +397,55 @@ def test_deferred_log_probs_far_samples_inactive_rows_and_graph_replay():
         _cabi.check(rc, "policy_fwd")
 
 
+@pytest.mark.parametrize("S", [4096, 100, 17])
+@pytest.mark.parametrize("B", [3, 12])
+def test_deferred_half_tile_ctas_are_bit_identical_to_both_256_thread_paths(S, B):
+    """A deferred launch runs as 128-thread CTAs of ONE half-tile (1024 scalars) whose reductions are spread over 8 sub-records per
+    sample; the 256-thread kernels convert each of their two half-tiles to fixed point on its own and add integers.  So the
+    deferred launch in either shape (mixgrpo_set_tuning key 6) and the immediate launch give the same bits — at the full size,
+    with a ragged last tile (n = 6400: 7 half-tiles, 4 tiles) and below one half-tile; far samples (side accumulators) included."""
+    from mixgrpo_b200 import _cabi, coefs, ops
+    from mixgrpo_b200._cabi import SRC_DETERMINISTIC, SRC_GIVEN, SRC_NOISE
+    d = _dev()
+    g = torch.Generator(device=d).manual_seed(77)
+    idx = 5
+    x = torch.randn(B, S, 64, device=d, generator=g)
+    v = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    e = torch.randn(B, S, 64, device=d, generator=g).bfloat16()
+    k, _ = coefs.flow(SIG, idx, ETA, "ref_cuda", True)
+    far = x + 3.0e4 * torch.randn(B, S, 64, device=d, generator=g)          # |d|/s ~ 1e5: every part goes to a side accumulator
+    far[1] = x[1] + 0.3 * torch.randn(S, 64, device=d, generator=g)         # ... except sample 1's
+    cases = [dict(src=SRC_DETERMINISTIC), dict(src=SRC_NOISE, noise=e), dict(src=SRC_GIVEN, x_next=far)]
+    lib = _cabi.lib()
+    for kw in cases:
+        imm = ops.fused_step(ops.FLOW, v, x, k, want_x0=False, round_like_torch=True, **kw)
+        got = {}
+        for half in (2, 0):                                              # 2 = the 128-thread shape whatever the grid size, 0 = never
+            old = lib.mixgrpo_set_tuning(6, half)
+            try:
+                acc = ops.DeferredLogProbs(d, 2, B, S * 64)
+                out = torch.zeros(2, B, device=d)
+                xn = torch.empty_like(x) if kw["src"] != SRC_GIVEN else None
+                ops.fused_step(ops.FLOW, v, x, k, want_x0=False, round_like_torch=True, out_x_next=xn, defer=acc.slot(1, k), **kw)
+                acc.finalize(out)
+            finally:
+                lib.mixgrpo_set_tuning(6, old)
+            assert torch.isnan(out[0]).all()
+            got[half] = out[1].clone()
+            if xn is not None:
+                assert torch.equal(xn, imm[0])
+        assert torch.isfinite(imm[2]).all()
+        assert torch.equal(got[2], imm[2]) and torch.equal(got[0], imm[2]), (kw["src"], got, imm[2])
+    # the default (key 6 = 1) picks the 128-thread shape only when the 256-thread grid is more than one wave of 6 CTAs per SM
+    sms = torch.cuda.get_device_properties(d).multi_processor_count
+    tiles = (S * 64 + 2047) // 2048
+    before = lib.mixgrpo_set_tuning(8, 0)
+    acc = ops.DeferredLogProbs(d, 2, B, S * 64)
+    ops.fused_step(ops.FLOW, v, x, k, want_x0=False, round_like_torch=True, src=SRC_DETERMINISTIC, defer=acc.slot(0, k))
+    acc.finalize(torch.zeros(2, B, device=d))
+    assert lib.mixgrpo_set_tuning(8, 0) - before == (1 if tiles * B > 6 * sms else 0)
+
+
 # ------------------------------------------------------------------------------------------ trajectory seed fused into step 0
 @pytest.mark.parametrize("first_sde", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
