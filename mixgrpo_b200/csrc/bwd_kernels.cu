@@ -36,14 +36,14 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
   float v[VEC], x[VEC], xn[VEC], t[VEC], mu[VEC], x0[VEC], g[VEC];
   if (active) {
     ld_stream(reinterpret_cast<const VT*>(p.v) + (long long)b * p.n + idx, v);
-    ld_stream(p.x + (long long)b * p.x_bs + idx, x);
-    ld_stream(p.x_next + (long long)b * p.in_bs + idx, xn);
+    ld_dep(p.x + (long long)b * p.x_bs + idx, x);
+    ld_dep(p.x_next + (long long)b * p.in_bs + idx, xn);
   }
   if constexpr (EARLY) pdl_prologue();
   if (!active) return;
   // (g/n)/(2 s^2): per-sample scalar, same two divisions autograd performs
-  float g_lp = __ldg(p.grad_logp + b);
-  if (p.loss.old_lp) g_lp = loss_terms(g_lp, __ldg(p.loss.old_lp + b), __ldg(p.loss.adv + b), p.loss, 1.f).grad;   // TR:560-585 in place
+  float g_lp = ld_dep(p.grad_logp + b);            // the forward launched just before wrote it: behind the wait, coherent
+  if (p.loss.old_lp) g_lp = loss_terms(g_lp, ld_dep(p.loss.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;   // TR:560-585 in place
   const float gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), p.k.two_var);
 
   if constexpr (FAM == 0) {   // flow, SU:186

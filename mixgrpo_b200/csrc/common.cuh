@@ -46,6 +46,30 @@ __device__ __forceinline__ void ld_stream(const __nv_bfloat16* p, float (&r)[1])
   r[0] = __bfloat162float(*p);
 }
 
+// Data the launch immediately BEFORE this one may have written — the latents a rollout step reads, a DPM history, the stored
+// x_next, the new log-probs a backward reads: COHERENT loads that are also compiler barriers.  ld.global.nc promises that the
+// data is read-only for the kernel's whole lifetime, which under programmatic dependent launch begins before the previous
+// kernel has ended; ptxas does move such loads across griddepcontrol.wait (it had put the wait of an early-loads launch right
+// in front of the kernel's first STORE), so .nc is only for streams produced several launches back (model output, noise).
+__device__ __forceinline__ void ld_dep(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld_dep(const float* p, float (&r)[1]) {
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r[0]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ float ld_dep(const float* p) {
+  float r;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned long long ld_dep(const unsigned long long* p) {
+  unsigned long long r;
+  asm volatile("ld.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+
 __device__ __forceinline__ void st_stream(float* p, const float (&r)[8]) {
   asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])

@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(256) global_adv_kernel(const float* __restrict
 // Clipped surrogate + KL over a batch of B log-probs, forward and dL/dnew_logp in one launch (TR:560-583).
 // One warp when B <= 32 (the usual case: no barrier at all), else 256 threads.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) grpo_loss_kernel(const float* __restrict__ new_lp, const float* __restrict__ old_lp,
-                                                           const float* __restrict__ adv, long long B, LossParams q,
+__global__ void __launch_bounds__(THREADS) grpo_loss_kernel(const float* new_lp, const float* old_lp,     // no __restrict__: the launch before may
+                                                           const float* adv, long long B, LossParams q,                  // have written them (no .nc loads, see ld_dep)
                                                            float* __restrict__ stats, float* __restrict__ grad,
                                                            float* __restrict__ accum) {
   pdl_prologue();

@@ -40,13 +40,14 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   const float* xp = q.x + (long long)b * q.x_bs;
   const float* ap = q.x_in + (long long)b * q.in_bs;
   float acc = 0.f;
+  const LpQuant lpq = lp_quant(n, q.k.two_var);
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * kTile + threadIdx.x * kVec;
     if (off >= n) continue;
     float v[kVec], x[kVec], a[kVec];
     ld_stream(vp + off, v);
-    ld_stream(xp + off, x);
-    ld_stream(ap + off, a);
+    ld_dep(xp + off, x);
+    ld_dep(ap + off, a);
     if (p.early != 0) pdl_prologue();               // grid.x == tiles: the first iteration is the only one
 #pragma unroll
     for (int j = 0; j < kVec; j += 2) {
@@ -57,15 +58,14 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
     }
   }
 
-  __shared__ float s_warp[kThreads / 32];
-  acc = warp_sum(acc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_warp[warp] = acc;
-  __syncthreads();
-  if (warp != 0) return;
+  __shared__ unsigned long long s_part[kThreads / 32];
   unsigned long long* rec = p.acc + kWsStride * (long long)blockIdx.y;
-  const unsigned long long add = cta_share(s_warp, lane, __fmul_rn((float)n, q.k.two_var), 2 * (int)gridDim.x, rec);   // step_math.cuh
-  if (lane == 0) {
+  const unsigned long long part = warp_part(acc, lpq, rec);                          // step_math.cuh: integer from the thread up
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  {
+    const unsigned long long add = cta_word<kThreads / 32>(s_part);
     const int ctas = gridDim.x;
     const unsigned long long old = atomicAdd(rec, add);
     if ((old & kArrivalMask) == (unsigned long long)(ctas - 1)) {
@@ -98,12 +98,12 @@ __global__ void __launch_bounds__(kThreads) policy_bwd_multi_kernel(const __grid
   float v[kVec], x[kVec], xn[kVec], t[kVec], g[kVec];
   if (active) {
     ld_stream(reinterpret_cast<const VT*>(q.v) + (long long)b * p.n + idx, v);
-    ld_stream(q.x + (long long)b * q.x_bs + idx, x);
-    ld_stream(q.x_in + (long long)b * q.in_bs + idx, xn);
+    ld_dep(q.x + (long long)b * q.x_bs + idx, x);
+    ld_dep(q.x_in + (long long)b * q.in_bs + idx, xn);
   }
   if (p.early != 0) pdl_prologue();
   if (!active) return;
-  const float g_lp = loss_terms(__ldg(q.logp + b), __ldg(q.old_lp + b), __ldg(p.loss.adv + b), p.loss, 1.f).grad;
+  const float g_lp = loss_terms(ld_dep(q.logp + b), ld_dep(q.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;   // the forward just wrote logp
   const float gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), q.k.two_var);
   if constexpr (FAM == kFlow) {
 #pragma unroll

@@ -9,7 +9,8 @@ namespace mg {
 
 // packed index: [b][hp][wp][c][dh][dw]   <->   unpacked: [b][c][2hp+dh][2wp+dw]
 template <class T, bool PACK, bool AFFINE>
-__global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ src, T* __restrict__ dst, long long total_pairs,
+__global__ void __launch_bounds__(256) pack_kernel(const T* src, T* __restrict__ dst,   // src: maybe the last step's output (no .nc loads, see ld_dep)
+                                                    long long total_pairs,
                                                   int C, int H, int W, float divisor, float shift) {
   pdl_prologue();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // one (dw=0,1) pair

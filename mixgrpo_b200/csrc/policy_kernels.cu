@@ -64,7 +64,7 @@ __device__ __forceinline__ unsigned long long global_ns_p() {
 // shared memory per CTA for K owned tiles: residuals as two float4 planes (conflict-free 128-bit accesses), then
 // per-tile warp partials, start epochs and per-tile backward scalars
 __host__ __device__ inline size_t policy_smem_bytes(int K) {
-  return (size_t)K * (kTile * sizeof(float) + (kThreads / 32) * sizeof(float) + sizeof(uint32_t) + sizeof(float));
+  return (size_t)K * (kTile * sizeof(float) + (kThreads / 32) * sizeof(unsigned long long) + sizeof(uint32_t) + sizeof(float));
 }
 
 // PF: software-prefetch the next tile's inputs into registers (<= 3 CTAs/SM); without it the kernel fits 42 registers
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   extern __shared__ __align__(16) unsigned char s_raw[];
   float4* s_lo = reinterpret_cast<float4*>(s_raw);                       // [Kmax][256] residuals 0..3 of each thread
   float4* s_hi = s_lo + (size_t)Kmax * kThreads;                         // [Kmax][256] residuals 4..7
-  float* s_part = reinterpret_cast<float*>(s_hi + (size_t)Kmax * kThreads);   // [Kmax][8] per-warp sums of d^2
+  unsigned long long* s_part = reinterpret_cast<unsigned long long*>(s_hi + (size_t)Kmax * kThreads);   // [Kmax][8] per-warp parts of the packed word
   uint32_t* s_e0 = reinterpret_cast<uint32_t*>(s_part + (size_t)Kmax * (kThreads / 32));   // [Kmax] epoch at kernel start
   float* s_gs = reinterpret_cast<float*>(s_e0 + Kmax);                   // [Kmax] (dL/dlogp / n) / (2 s^2) of the tile's sample
 
@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   const int t_lo = (int)(((long long)blockIdx.x * p.T) / gridDim.x), t_hi = (int)(((long long)(blockIdx.x + 1) * p.T) / gridDim.x);
   const int K = t_hi - t_lo;                                             // 1 <= K <= Kmax (host guarantees G <= T)
   const int n = (int)p.n;
+  const LpQuant lpq = lp_quant(p.n, p.k.two_var);
   const VT* vbase = reinterpret_cast<const VT*>(p.v);
 
   if (tid < K) s_e0[tid] = ld_relaxed_gpu(p.epoch + 2 * kWsStride * ((t_lo + tid) / p.tps));
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
     tile_pos(k, b, off);
     if (off >= n) return false;
     ld_stream(vbase + ((long long)b * n + off), vv);
-    ld_stream(p.x + ((long long)b * p.x_bs + off), xx);
-    ld_stream(p.x_next + ((long long)b * p.in_bs + off), aa);
+    ld_dep(p.x + ((long long)b * p.x_bs + off), xx);
+    ld_dep(p.x_next + ((long long)b * p.in_bs + off), aa);
     return true;
   };
   if constexpr (PF) act = load_tile(0, v, x, a);
@@ -134,8 +135,12 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
     }
     s_lo[(size_t)k * kThreads + tid] = make_float4(d[0], d[1], d[2], d[3]);
     s_hi[(size_t)k * kThreads + tid] = make_float4(d[4], d[5], d[6], d[7]);
-    acc = warp_sum(acc);
-    if (lane == 0) s_part[k * (kThreads / 32) + warp] = acc;
+    {
+      int bk, offk;
+      tile_pos(k, bk, offk);
+      const unsigned long long part = warp_part(acc, lpq, p.acc + kWsStride * bk);      // step_math.cuh: integer from the thread up
+      if (lane == 0) s_part[k * (kThreads / 32) + warp] = part;
+    }
     if constexpr (PF) {
       if (k + 1 < K) {
 #pragma unroll
@@ -150,10 +155,8 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   int my_b = 0;
   if (tid < K) {
     my_b = (t_lo + tid) / p.tps;
-    const float* w = s_part + tid * (kThreads / 32);
     unsigned long long* rec = p.acc + kWsStride * my_b;
-    // mg::step_kernel's arithmetic: each half-tile's four warp sums in its xor-shuffle order, fixed point per half (step_math.cuh)
-    const unsigned long long add = cta_share_serial(w, __fmul_rn((float)n, p.k.two_var), 2 * p.tps, rec);
+    const unsigned long long add = cta_word<kThreads / 32>(s_part + tid * (kThreads / 32));
     const unsigned long long old = atomicAdd(rec, add);
     if ((old & kArrivalMask) == (unsigned long long)(p.tps - 1)) {
       const float q = packed_total(old + add, rec);
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
     }
     if (ready) {
       const float lp = ld_relaxed_gpu(p.logp_out + my_b);
-      const float g_lp = loss_terms(lp, __ldg(p.loss.old_lp + my_b), __ldg(p.loss.adv + my_b), p.loss, 1.f).grad;   // TR:560-585
+      const float g_lp = loss_terms(lp, ld_dep(p.loss.old_lp + my_b), ld_dep(p.loss.adv + my_b), p.loss, 1.f).grad;   // TR:560-585
       gs = __fdiv_rn(__fdiv_rn(g_lp, (float)n), p.k.two_var);            // (g/n)/(2 s^2): the two divisions autograd performs
     }
     s_gs[tid] = gs;

@@ -35,7 +35,6 @@ struct StepParams {
   unsigned long long* acc;
   long long n, x_bs, in_bs, out_bs;
   int B, tiles;
-  int parts;                // half-tiles per sample of the 256-thread tiling = 2 x (256-thread CTAs per sample): the cap of packed_part
   mixgrpo_step_coefs k;
   unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
   const unsigned long long* philox_state;          // SRC_PHILOX, graph-safe: device {seed, base offset} (or nullptr)
@@ -89,16 +88,19 @@ __device__ __forceinline__ void store_decoded(const StepParams& p, int b, long l
 //   goes into the record's 64-bit side accumulators instead (packed_share / packed_total in step_math.cuh), so the
 //   log-prob stays finite like the reference's up to |d|/s ~ 4e7; only a non-finite share (or one beyond that) gives NaN.
 
-template <class T, bool VECTOR>
+// DEP: the stream may have been written by the launch immediately before this one (latents, DPM history, stored x_next) ->
+// coherent loads that stay behind griddepcontrol.wait (ld_dep, common.cuh); model output and noise come from several launches back
+template <class T, bool VECTOR, bool DEP = false>
 __device__ __forceinline__ void load_tile(const T* base, long long off, long long n, float (&r)[kVec]) {
   if constexpr (VECTOR) {
-    ld_stream(base + off + threadIdx.x * kVec, r);          // caller guarantees off + 8t < n
+    if constexpr (DEP) ld_dep(base + off + threadIdx.x * kVec, r);          // caller guarantees off + 8t < n
+    else ld_stream(base + off + threadIdx.x * kVec, r);
   } else {
 #pragma unroll
     for (int j = 0; j < kVec; ++j) {
       const long long i = off + j * kThreads + threadIdx.x;
       float one[1] = {0.f};
-      if (i < n) ld_stream(base + i, one);
+      if (i < n) { if constexpr (DEP) ld_dep(base + i, one); else ld_stream(base + i, one); }
       r[j] = one[0];
     }
   }
@@ -139,6 +141,7 @@ step_kernel(const __grid_constant__ StepParams p) {
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
   const float* xp = p.x + (long long)b * p.x_bs;
   float acc = 0.f;
+  const LpQuant lpq = lp_quant(n, p.k.two_var);     // a division, done while nothing has arrived yet
 
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * TILE;
@@ -149,10 +152,10 @@ step_kernel(const __grid_constant__ StepParams p) {
     if constexpr (SRC == MIXGRPO_SRC_NOISE) load_tile<NT, VECTOR>(reinterpret_cast<const NT*>(p.noise) + (long long)b * n, off, n, a);
     if (p.early == 1) pdl_prologue();
     if constexpr (EXT == 2) load_tile<__nv_bfloat16, VECTOR>(reinterpret_cast<const __nv_bfloat16*>(p.x) + (long long)b * p.x_bs, off, n, x);
-    else load_tile<float, VECTOR>(xp, off, n, x);
+    else load_tile<float, VECTOR, true>(xp, off, n, x);
     if constexpr (SRC == MIXGRPO_SRC_PHILOX) {     // draw the noise here: element e -> component e%4 of Philox(e/4)
       unsigned long long ph_seed = p.philox_seed, ph_off = p.philox_offset;
-      if (p.philox_state) { ph_seed = __ldg(p.philox_state); ph_off += __ldg(p.philox_state + 1); }   // graph-safe state
+      if (p.philox_state) { ph_seed = ld_dep(p.philox_state); ph_off += ld_dep(p.philox_state + 1); }   // graph-safe state (moved by mixgrpo_philox_advance)
       if constexpr (VECTOR) {
         const unsigned long long e0 = (unsigned long long)b * n + off + threadIdx.x * kVec;
         float z0[4], z1[4];
@@ -171,9 +174,9 @@ step_kernel(const __grid_constant__ StepParams p) {
       }
       if constexpr (sizeof(NT) == 2) round_like_torch<true>(a);        // the noise tensor itself is bf16 (SU:193)
     }
-    if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR>(p.x_in + (long long)b * p.in_bs, off, n, a);
-    if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR>(p.m1 + (long long)b * n, off, n, m1);
-    if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR>(p.m2 + (long long)b * n, off, n, m2);
+    if constexpr (SRC == MIXGRPO_SRC_GIVEN) load_tile<float, VECTOR, true>(p.x_in + (long long)b * p.in_bs, off, n, a);
+    if constexpr (FAM == kDpm && ORDER >= 2) load_tile<float, VECTOR, true>(p.m1 + (long long)b * n, off, n, m1);
+    if constexpr (FAM == kDpm && ORDER == 3) load_tile<float, VECTOR, true>(p.m2 + (long long)b * n, off, n, m2);
     if (p.early == 2) pdl_prologue();
 
     float xn[kVec], x0[OUT >= 1 ? kVec : 2], mu[OUT == 2 ? kVec : 2];
@@ -206,31 +209,23 @@ step_kernel(const __grid_constant__ StepParams p) {
   }
   if (p.logp_out == nullptr && !p.defer) return;
 
-  __shared__ float s_warp[(HALF ? kHalfThreads : kThreads) / 32];
-  acc = warp_sum(acc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_warp[warp] = acc;
-  __syncthreads();
-  if (warp != 0) return;                           // the other warps are done: nothing waits on the atomic
-  const float denom = __fmul_rn((float)n, p.k.two_var);
-  // a deferred launch spreads a sample's arrivals over kDeferSubs records; side words of the same sub-record
+  constexpr int WARPS = (HALF ? kHalfThreads : kThreads) / 32;
+  __shared__ unsigned long long s_part[WARPS];
+  // a deferred launch spreads a sample's arrivals over kDeferSubs records (side words of the same sub-record)
   unsigned long long* rec = p.defer ? p.acc + ((long long)kDeferSubs * b + (blockIdx.x & (kDeferSubs - 1))) * kWsStride : p.acc + kWsStride * b;
-  if constexpr (HALF) {
-    const float t = half_sum(s_warp, lane);
-    if (lane == 0) {
-      const unsigned long long add = packed_part(__fdiv_rn(t, denom), p.parts, rec) + 1ull;
-      asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(rec), "l"(add) : "memory");
-    }
-  } else {
-  const unsigned long long add = cta_share(s_warp, lane, denom, p.parts, rec);
-  if (lane == 0) {
-    const int ctas = gridDim.x;
-    if (p.defer) {
+  const unsigned long long part = warp_part(acc, lpq, rec);                        // step_math.cuh: integer from the thread up
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x != 0) return;                    // nothing else waits on the atomic
+  {
+    const unsigned long long add = cta_word<WARPS>(s_part);
+    if (HALF || p.defer) {
       // a true reduction (REDG.E.ADD.64): nothing comes back, so the CTA retires without an L2 round trip; the sums are
       // turned into log-probs by mixgrpo_logp_finalize after the rollout.  Spelled in PTX: nvcc keeps an ATOMG otherwise.
       asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(rec), "l"(add) : "memory");
       return;
     }
+    const int ctas = gridDim.x;
     const unsigned long long old = atomicAdd(rec, add);
     if ((old & kArrivalMask) == (unsigned long long)(ctas - 1)) {
       const float q = packed_total(old + add, rec);
@@ -253,7 +248,6 @@ step_kernel(const __grid_constant__ StepParams p) {
       }
     }
   }
-  }  // !HALF
 }
 
 // ------------------------------------------------------------------ host-side dispatch
@@ -269,7 +263,6 @@ template <int FAM, class VT, class NT, int SRC, int ORDER, bool RND, bool SDE, b
 static int launch(StepParams& p, cudaStream_t st) {
   p.tiles = (int)((p.n + kTile - 1) / kTile);
   int ctas = p.tiles < g_max_ctas_per_sample ? p.tiles : g_max_ctas_per_sample;
-  p.parts = 2 * ctas;
   if constexpr (VECTOR) {
     // a rollout's deferred launches: one 128-thread CTA per half-tile (never looping, so the parts are the same half-tiles) —
     // when the 256-thread grid is more than one wave of 6 CTAs per SM.  Measured (B200): (12,4096,64) 1536 CTAs -0.2 us of 6.15,
@@ -351,7 +344,7 @@ static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_
   p.x_out = x_out; p.x0_out = x0_out; p.mean_out = mean_out; p.logp_out = logp_out;
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
-  p.B = (int)B; p.tiles = 0; p.parts = 0; p.k = *k;
+  p.B = (int)B; p.tiles = 0; p.k = *k;
   p.philox_seed = p.philox_offset = 0ull;
   p.philox_state = nullptr;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};

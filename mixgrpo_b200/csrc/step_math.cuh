@@ -10,13 +10,14 @@ namespace mg {
 
 enum Family { kFlow = 0, kDance = 1, kDpm = 2 };
 
-// packed log-prob accumulator (one 64-bit word per sample): [ sum Q8.32 : 40 | wide-part count : 12 | arrivals : 12 ]
+// packed log-prob accumulator (one 64-bit word per sample): [ sum Q8.32 : 40 | wide flag count : 12 | arrivals : 12 ]
 constexpr int kTile = kThreads * kVec;          // scalars per CTA-tile of the 256-thread kernels
 constexpr int kHalfThreads = kThreads / 2;      // the 128-thread (4-warp) CTA of the deferred rollout kernels ...
-constexpr int kHalfTile = kHalfThreads * kVec;  // ... owns one HALF-tile: 1024 consecutive scalars
+constexpr int kHalfTile = kHalfThreads * kVec;  // ... owns one half-tile: 1024 consecutive scalars
 constexpr int kCountBits = 12, kPoisonBits = 12;
 constexpr unsigned long long kArrivalMask = (1ull << kCountBits) - 1;
-// a CTA contributes two parts (its half-tiles), each of which may be counted in the 12-bit "wide" field: <= 2047 CTAs per sample
+constexpr unsigned long long kWideMask = ((1ull << kPoisonBits) - 1) << kCountBits;
+// a sample's CTAs each add one arrival and at most one wide flag; 128-thread CTAs are twice as many: <= 2047 256-thread CTAs per sample
 constexpr int kMaxCtasPerSample = (1 << (kCountBits - 1)) - 1;
 // workspace record per sample (in 64-bit words): { accumulator, { epoch : 32 | status : 32 }, wide side accumulator, integer side
 // accumulator } — see mixgrpo_step_workspace_bytes.  A DEFERRED launch (MIXGRPO_FLAG_DEFER_LOGP) spreads a sample's arrivals over
@@ -26,69 +27,64 @@ constexpr int kWsStride = 4;
 constexpr int kWsWide = 2;                      // word index of the side accumulator inside a record
 constexpr int kWsHuge = 3;                      // word index of the second side accumulator (integer units)
 constexpr int kDeferSubs = 8;
-constexpr float kWideCap = 134217728.f;         // 2^27: largest share the Q39.24 side accumulator takes (4094 parts x 2^27 x 2^24 < 2^63)
-constexpr float kHugeCap = 1125899906842624.f;  // 2^50: largest share the integer side accumulator takes (4094 x 2^50 < 2^63)
+constexpr float kWideCap = 16777216.f;          // 2^24: largest warp part the Q39.24 side accumulator takes (16376 warps x 2^24 x 2^24 < 2^63)
+constexpr float kHugeCap = 281474976710656.f;   // 2^48: largest warp part the integer side accumulator takes (16376 x 2^48 < 2^63)
 
-// The unit of the reduction is the HALF-TILE: the 1024 consecutive scalars four warps own.  Its d^2 sum is taken in fp32 in a
-// fixed order (per thread pair-wise, five xor-shuffle levels per warp, two over the four warp sums), scaled to
-// r = sum / (n * 2 s^2) and converted to Q8.32 fixed point ON ITS OWN; everything above that level is integer addition, which
-// commutes.  So a 256-thread CTA (two half-tiles, added as integers before its one atomic), a 128-thread CTA of the deferred
-// rollout kernels (one half-tile, one fire-and-forget reduction), the batched window kernel and the single-pass policy kernel
-// all produce bit-identical log-probs, in any arrival order.
+// The log-prob reduction is INTEGER from the thread up.  A thread's sum of d^2 over its 8 scalars (fp32, pair-wise, fixed
+// order) is scaled by 2^32 / (n * 2 s^2) and rounded to an unsigned integer — its share of mean(d^2 / 2 s^2) in units of 2^-32
+// — and everything above is integer addition, which commutes: ONE redux.sync.add.u32 per warp instead of five dependent
+// shuffles, a 64-bit word per warp through shared memory, one atomic (or fire-and-forget reduction) per CTA.  So any CTA
+// shape, any arrival order and any of the kernels that evaluate the same transition — the 256-thread step / policy kernels, the
+// 128-thread deferred rollout shape, the batched window kernel, the single-pass policy kernel — give bit-identical log-probs.
+// Rounding per thread costs <= 0.5 unit each: 0.29 * sqrt(n/8) units in total = 1.2e-8 absolute on a log-prob at 1024^2.
 //
-// The packed word holds parts of mean(d^2 / 2 s^2) up to 255/parts each — ample for any transition a sane policy
-// produces (the value is ~0.5 on the rollout's own samples).  The reference, though, returns a FINITE log-prob however far
-// x_next is from the mean (SU:201-208), so a part that does not fit is not dropped: it goes, as Q39.24 fixed point, into
-// the record's 64-bit side accumulator (integer adds: still order-independent, still bitwise reproducible) and only flags the
-// fact in the packed word's 12-bit "wide" count.  The finalizer folds the side word in and re-zeroes it.  A part above 2^27
-// (|d|/s > 16000) goes, rounded to an integer (relative resolution 2^-27), into a second side word; only a non-finite /
-// negative part, or one above 2^50 (|d|/s > 4e7, where the reference's own fp32 mean has long lost its digits), yields NaN.
-// The common path is unchanged: one atomic per CTA, no fence.
-// Returns the part's bits WITHOUT an arrival; `parts` = half-tiles per sample of the 256-thread tiling (2 x CTAs per sample).
-__device__ __forceinline__ unsigned long long packed_part(float r, int parts, unsigned long long* rec) {
-  const float cap = 255.0f / (float)parts;
-  unsigned long long add = 0ull;
-  if (!(r >= 0.f && r <= cap)) {
-    if (r > cap && r <= kWideCap) atomicAdd(rec + kWsWide, __float2ull_rn(r * 16777216.0f));
+// A thread's share must stay below `cap` = min(2^26, 255 * 2^32 / threads-per-sample): 32 lanes fit the 32-bit redux and a
+// whole sample fits the 40-bit field (total < 255).  That is |x' - mean| / s up to ~8..23 on EVERY scalar of a thread — ample for
+// any transition a sane policy produces (the value is ~1 on the rollout's own samples).  The reference, though, returns a FINITE
+// log-prob however far x_next is from the mean (SU:201-208), so a warp with a thread beyond the cap is not dropped: its fp32
+// sum goes, as Q39.24 fixed point, into the record's 64-bit side accumulator (integer adds: still order-independent, still
+// bitwise reproducible), above 2^24 rounded to an integer into a second side word, and the warp raises the word's "wide"
+// flag; the finalizer folds the side words in and re-zeroes them.  Only a non-finite sum, or one above 2^48 (|d|/s > 1e8,
+// where the reference's own fp32 mean has long lost its digits), yields NaN.  The common path has no branch but the vote.
+struct LpQuant { float scale, cap, denom; };
+__device__ __forceinline__ LpQuant lp_quant(long long n, float two_var) {       // evaluated while the loads are in flight
+  LpQuant q;
+  q.denom = __fmul_rn((float)n, two_var);
+  q.scale = __fdiv_rn(4294967296.f, q.denom);
+  q.cap = fminf(67108864.f, __fdiv_rn(1095216660480.f, (float)((n + kVec - 1) / kVec)));     // 255 * 2^32 / threads per sample
+  return q;
+}
+
+// All 32 lanes of a warp: acc = the thread's sum of d^2.  Returns (in every lane) the warp's part of the packed word — the
+// fixed-point sum in the upper 40 bits, or zero there and one wide flag when the warp went to the side accumulators of `rec`.
+__device__ __forceinline__ unsigned long long warp_part(float acc, const LpQuant& q, unsigned long long* rec) {
+  const float u = __fmul_rn(acc, q.scale);
+  if (__all_sync(0xffffffffu, u < q.cap))                                         // NaN fails the test
+    return (unsigned long long)__reduce_add_sync(0xffffffffu, __float2uint_rn(u)) << (kCountBits + kPoisonBits);
+  const float r = __fdiv_rn(warp_sum(acc), q.denom);                              // far transition: fp32 warp sum, side words
+  if ((threadIdx.x & 31) == 0) {
+    if (r >= 0.f && r <= kWideCap) atomicAdd(rec + kWsWide, __float2ull_rn(r * 16777216.0f));
     else if (r > kWideCap && r <= kHugeCap) atomicAdd(rec + kWsHuge, __float2ull_rn(r));
     else atomicOr(rec + kWsWide, 1ull << 63);
     __threadfence();                             // the side word is visible before this CTA's arrival is counted
-    add = 1ull << kCountBits;
-    r = 0.f;
   }
-  return add + (__float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits));
+  return 1ull << kCountBits;
 }
 
-// Warp 0 of a 256-thread CTA, all 32 lanes: s_warp = the 8 warp sums of d^2 (warps 0-3 = first half-tile, 4-7 = second).
-// Returns, in lane 0, the word the CTA adds to its sample's record: one arrival + both half-tile parts.
-static_assert(kThreads / 32 == 8, "cta_share assumes 8 warps per CTA");
-__device__ __forceinline__ unsigned long long cta_share(const float* s_warp, int lane, float denom, int parts, unsigned long long* rec) {
-  float t = lane < 8 ? s_warp[lane] : 0.f;
-  t += __shfl_xor_sync(0xffffffffu, t, 2);
-  t += __shfl_xor_sync(0xffffffffu, t, 1);        // lanes 0 and 4: (w0 + w2) + (w1 + w3) of their half
-  unsigned long long add = 0ull;
-  if (lane == 0 || lane == 4) add = packed_part(__fdiv_rn(t, denom), parts, rec);
-  add += __shfl_down_sync(0xffffffffu, add, 4);
-  return add + 1ull;
-}
-// the same two values from the 8 warp sums held by ONE thread (single-pass policy kernel)
-__device__ __forceinline__ unsigned long long cta_share_serial(const float* w, float denom, int parts, unsigned long long* rec) {
-  const float h0 = __fadd_rn(__fadd_rn(w[0], w[2]), __fadd_rn(w[1], w[3]));
-  const float h1 = __fadd_rn(__fadd_rn(w[4], w[6]), __fadd_rn(w[5], w[7]));
-  return packed_part(__fdiv_rn(h0, denom), parts, rec) + packed_part(__fdiv_rn(h1, denom), parts, rec) + 1ull;
-}
-// warp 0 of a 128-thread CTA: s_warp = its 4 warp sums; lane 0 gets the half-tile's sum in the same order
-__device__ __forceinline__ float half_sum(const float* s_warp, int lane) {
-  float t = lane < 4 ? s_warp[lane] : 0.f;
-  t += __shfl_xor_sync(0xffffffffu, t, 2);
-  t += __shfl_xor_sync(0xffffffffu, t, 1);
-  return t;
+// One thread: the word a CTA adds to its sample's record from its WARPS warp parts — their integer sum, at most ONE wide flag
+// (flags only say "read the side words"; counting CTAs keeps the 12-bit field from overflowing), one arrival.
+template <int WARPS>
+__device__ __forceinline__ unsigned long long cta_word(const unsigned long long* parts) {
+  unsigned long long t = 0ull;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) t += parts[w];
+  return (t & ~kWideMask) + ((t & kWideMask) ? (1ull << kCountBits) : 0ull) + 1ull;
 }
 
 // tot = the packed word after the LAST arrival; returns mean(d^2 / 2 s^2) of the sample
 __device__ __forceinline__ float packed_total(unsigned long long tot, unsigned long long* rec) {
   double q = (double)(tot >> (kCountBits + kPoisonBits)) * (1.0 / 4294967296.0);
-  if ((tot >> kCountBits) & ((1ull << kPoisonBits) - 1)) {
+  if (tot & kWideMask) {
     __threadfence();
     const unsigned long long wide = atomicExch(rec + kWsWide, 0ull);      // read and leave zeroed for the next launch
     const unsigned long long huge = atomicExch(rec + kWsHuge, 0ull);

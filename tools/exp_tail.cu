@@ -18,11 +18,23 @@ int mixgrpo_peer_set_timeout_ms(int) { return 0; }
 int mixgrpo_policy_set_tuning(int, int) { return 0; }
 extern "C" int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t) { return B * 32; }
 extern "C" int64_t mixgrpo_deferred_workspace_bytes(int64_t B, int64_t) { return B * 256; }
-namespace mg { int g_half_ctas = 0; }
+namespace mg { int g_half_ctas = 0; long long g_half_launches = 0; int g_bwd_threads = 256; int sm_count() { return 148; } }
 
 using namespace mg;
 
 
+
+// the CTA-level conversion the float variants use (what shipped before the reduction became integer from the thread up)
+__device__ __forceinline__ unsigned long long exp_packed_part(float r, int parts, unsigned long long* rec) {
+  const float cap = 255.0f / (float)parts;
+  unsigned long long add = 0ull;
+  if (!(r >= 0.f && r <= cap)) {
+    atomicAdd(rec + kWsWide, __float2ull_rn(r * 16777216.0f));
+    add = 1ull << kCountBits;
+    r = 0.f;
+  }
+  return add + (__float2ull_rn(r * 4294967296.0f) << (kCountBits + kPoisonBits));
+}
 
 __device__ __forceinline__ void red_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
@@ -80,13 +92,13 @@ __global__ void __launch_bounds__(THREADS, MINB) ode_exp_kernel(const __grid_con
     for (int o = WARPS / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) {
       const float r = __fdiv_rn(t, __fmul_rn((float)n, p.k.two_var));
-      red_u64(TAIL == 6 ? mine : rec, packed_part(r, 2 * (int)gridDim.x, rec) + 1ull);
+      red_u64(TAIL == 6 ? mine : rec, exp_packed_part(r, 2 * (int)gridDim.x, rec) + 1ull);
     }
   } else if constexpr (TAIL == 1) {
     acc = warp_sum(acc);
     if (lane == 0) {
       const float r = __fdiv_rn(acc, __fmul_rn((float)n, p.k.two_var));
-      red_u64(mine, packed_part(r, 2 * per_sub, rec) + 1ull);
+      red_u64(mine, exp_packed_part(r, 2 * per_sub, rec) + 1ull);
     }
   } else if constexpr (TAIL == 2) {
     const float q = acc * scale;                               // units of 2^-32 of mean(d^2 / 2 s^2)
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ode_exp_kernel(const __grid_con
       acc = warp_sum(acc);
       if (lane == 0) {
         const float r = __fdiv_rn(acc, __fmul_rn((float)n, p.k.two_var));
-        red_u64(mine, packed_part(r, 2 * per_sub, rec) + 1ull);
+        red_u64(mine, exp_packed_part(r, 2 * per_sub, rec) + 1ull);
       }
     }
   } else if constexpr (TAIL == 3 || TAIL == 5) {
@@ -141,6 +153,8 @@ extern "C" __attribute__((visibility("default"))) const char* exp_variant_name(i
     case 12: return "T6 shuffles+smem+barrier, 1 RED/CTA -> 16 lines           (256 thr, 6/SM)";
     case 13: return "T6 shuffles+smem+barrier, 1 RED/CTA -> 16 lines           (128 thr, 8/SM)";
     case 14: return "T6 shuffles+smem+barrier, 1 RED/CTA -> 4 lines            (128 thr, 12/SM)";
+    case 15: return "PRODUCT mg::step_kernel, 128-thread half-tile shape       (128 thr, 12/SM)";
+    case 16: return "PRODUCT mg::step_kernel, 256-thread shape, 8 sub-records  (256 thr, 6/SM)";
   }
   return nullptr;
 }
@@ -170,6 +184,8 @@ extern "C" __attribute__((visibility("default"))) int exp_ode(int variant, const
     case 12: return go<6, 256, 6, 1>(p, s, scale, st, 16, 16);
     case 13: return go<6, 128, 8, 1>(p, s, scale, st, 16, 16);
     case 14: return go<6, 128, 12, 1>(p, s, scale, st, 4, 16);
+    case 15: g_half_ctas = 2; p.acc = s; return launch<kFlow, __nv_bfloat16, __nv_bfloat16, MIXGRPO_SRC_DETERMINISTIC, 1, true, false, true, 0, 0>(p, st);
+    case 16: g_half_ctas = 0; p.acc = s; return launch<kFlow, __nv_bfloat16, __nv_bfloat16, MIXGRPO_SRC_DETERMINISTIC, 1, true, false, true, 0, 0>(p, st);
   }
   return MIXGRPO_EINVAL;
 }
