@@ -19,6 +19,7 @@ struct MultiItem {
   void* grad_v;
   long long x_bs, in_bs;
   mixgrpo_step_coefs k;
+  LpQuant lpq;              // host-evaluated (step_math.cuh)
 };
 
 struct MultiParams {
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
   const float* xp = q.x + (long long)b * q.x_bs;
   const float* ap = q.x_in + (long long)b * q.in_bs;
   float acc = 0.f;
-  const LpQuant lpq = lp_quant(n, q.k.two_var);
+  const LpQuant lpq = q.lpq;
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * kTile + threadIdx.x * kVec;
     if (off >= n) continue;
@@ -170,7 +171,7 @@ static int fill_multi(MultiParams& p, int family, int v_dtype, const mixgrpo_pol
     vec = vec && (s.x_bs % kVec == 0) && (s.in_bs % kVec == 0) && al(s.v, va) && al(s.x, 32) && al(s.x_next, 32) && (!backward || al(s.grad_v, va));
     MultiItem& d = p.it[j];
     d.v = s.v; d.x = s.x; d.x_in = s.x_next; d.logp = s.logp; d.old_lp = s.old_logp; d.rows = s.stats_rows; d.grad_v = s.grad_v;
-    d.x_bs = s.x_bs; d.in_bs = s.in_bs; d.k = s.coefs;
+    d.x_bs = s.x_bs; d.in_bs = s.in_bs; d.k = s.coefs; d.lpq = lp_quant(n, s.coefs.two_var);
   }
   if (!vec) return MIXGRPO_EUNSUPPORTED;
   p.n = n; p.B = (int)B; p.n_items = n_items; p.early = 0; p.acc = nullptr;

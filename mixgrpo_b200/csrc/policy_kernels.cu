@@ -35,6 +35,7 @@ struct PolicyStepParams {
   long long n, x_bs, in_bs, T; // T = B * tps tiles in total
   int B, tps;                  // tiles per sample
   mixgrpo_step_coefs k;
+  LpQuant lpq;                 // host-evaluated (step_math.cuh)
   LossParams loss;
   unsigned long long timeout_ns;
 };
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   const int t_lo = (int)(((long long)blockIdx.x * p.T) / gridDim.x), t_hi = (int)(((long long)(blockIdx.x + 1) * p.T) / gridDim.x);
   const int K = t_hi - t_lo;                                             // 1 <= K <= Kmax (host guarantees G <= T)
   const int n = (int)p.n;
-  const LpQuant lpq = lp_quant(p.n, p.k.two_var);
+  const LpQuant lpq = p.lpq;
   const VT* vbase = reinterpret_cast<const VT*>(p.v);
 
   if (tid < K) s_e0[tid] = ld_relaxed_gpu(p.epoch + 2 * kWsStride * ((t_lo + tid) / p.tps));
@@ -331,6 +332,7 @@ extern "C" __attribute__((visibility("default"))) int mixgrpo_policy_step(int fa
   p.status = reinterpret_cast<uint32_t*>(p.acc) + 3;
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.B = (int)B; p.tps = (int)tps; p.T = (long long)B * tps;
   p.k = *coefs_host;
+  p.lpq = lp_quant(n, coefs_host->two_var);
   p.loss = make_loss_params(loss->old_logp, loss->advantages, loss->stats_rows, loss->clip_range, loss->adv_clip_max, loss->kl_coeff, loss->denom);
   p.loss.accumulate = loss->accumulate ? 1 : 0;
   p.timeout_ns = g_policy_timeout_ms * 1000000ull;

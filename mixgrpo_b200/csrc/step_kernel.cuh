@@ -13,9 +13,11 @@
 // same bf16 rounding points when MIXGRPO_FLAG_ROUND_LIKE_TORCH is set, so x_next / x0 / mean are
 // bit-identical to the reference on identical inputs.  Only the log-prob reduction order differs.
 //
-// log-prob: per-thread sum of (x_next-mean)^2 -> warp shuffle -> half-tile (4 warps) -> fixed point -> ONE packed atomicAdd per
-// CTA (count + sum in a 64-bit word): order-independent, hence bitwise reproducible; the last arriver
-// writes logp[b] and re-zeroes the word (graph-replay safe).  Details at step_kernel below and in step_math.cuh.
+// log-prob: per-thread sum of (x_next-mean)^2 -> fixed point -> ONE redux.sync.add per warp -> 64-bit warp parts through shared
+// memory -> ONE packed atomicAdd per CTA (count + sum in a 64-bit word): integer from the thread up, so order- and
+// shape-independent, hence bitwise reproducible; the last arriver writes logp[b] and re-zeroes the word (graph-replay safe),
+// or — a rollout's deferred launches — nobody does and one finalize launch writes all log-probs.  Details at step_kernel below
+// and in step_math.cuh.
 #pragma once
 #include "step_math.cuh"
 
@@ -35,6 +37,7 @@ struct StepParams {
   unsigned long long* acc;
   long long n, x_bs, in_bs, out_bs;
   int B, tiles;
+  LpQuant lpq;              // fixed-point scale / per-thread cap / n * 2 s^2 of the log-prob reduction (host-evaluated, step_math.cuh)
   mixgrpo_step_coefs k;
   unsigned long long philox_seed, philox_offset;   // SRC_PHILOX
   const unsigned long long* philox_state;          // SRC_PHILOX, graph-safe: device {seed, base offset} (or nullptr)
@@ -78,15 +81,16 @@ __device__ __forceinline__ void store_decoded(const StepParams& p, int b, long l
 // without waiting on anything (a persistent / software-pipelined variant and every fence+ticket
 // reduction were 20-30 % slower).
 //
-// log-prob reduction — one atomic per CTA, deterministic, no fence:
-//   acc[b] is a 64-bit word  [ sum : 40 bit fixed point Q8.32 | poison : 12 | arrivals : 12 ].
-//   A CTA adds  (1, poison?, round(r * 2^32))  with r = sum_cta(d^2) / (n * 2 s^2)  in ONE atomicAdd.
-//   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in; the CTA
-//   whose returned count is the last one owns the complete sum in (old + mine), writes
+// log-prob reduction — one atomic per CTA, deterministic, no fence (step_math.cuh):
+//   acc[b] is a 64-bit word  [ sum : 40 bit fixed point Q8.32 | wide flags : 12 | arrivals : 12 ].
+//   A thread converts its sum of d^2 to units of 2^-32 of mean(d^2 / 2 s^2); a warp adds its 32 integers with ONE
+//   redux.sync; thread 0 adds the CTA's warp parts and issues ONE atomicAdd of (sum, wide?, 1 arrival).
+//   Integer addition commutes, so the total is bit-identical whatever order CTAs arrive in and whatever the CTA shape; the
+//   CTA whose returned count is the last one owns the complete sum in (old + mine), writes
 //   logp[b] = -sum - log s - log sqrt(2 pi) and zeroes the word for the next launch.
-//   Resolution 2^-32 per CTA (<= 1.5e-8 absolute on logp at 1024^2).  A share too large for the field (> 255/ctas)
-//   goes into the record's 64-bit side accumulators instead (packed_share / packed_total in step_math.cuh), so the
-//   log-prob stays finite like the reference's up to |d|/s ~ 4e7; only a non-finite share (or one beyond that) gives NaN.
+//   Resolution 2^-32 per thread (1.2e-8 absolute on logp at 1024^2).  A warp with a thread beyond the fixed-point range sends
+//   its fp32 sum to the record's 64-bit side accumulators instead, so the log-prob stays finite like the reference's up to
+//   |d|/s ~ 1e8; only a non-finite sum (or one beyond that) gives NaN.
 
 // DEP: the stream may have been written by the launch immediately before this one (latents, DPM history, stored x_next) ->
 // coherent loads that stay behind griddepcontrol.wait (ld_dep, common.cuh); model output and noise come from several launches back
@@ -141,7 +145,7 @@ step_kernel(const __grid_constant__ StepParams p) {
   const VT* vp = reinterpret_cast<const VT*>(p.v) + (long long)b * n;
   const float* xp = p.x + (long long)b * p.x_bs;
   float acc = 0.f;
-  const LpQuant lpq = lp_quant(n, p.k.two_var);     // a division, done while nothing has arrived yet
+  const LpQuant lpq = p.lpq;
 
   for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
     const long long off = (long long)tile * TILE;
@@ -345,6 +349,7 @@ static inline void fill(StepParams& p, const void* v, const float* x, int64_t x_
   p.acc = reinterpret_cast<unsigned long long*>(ws);
   p.n = n; p.x_bs = x_bs; p.in_bs = in_bs; p.out_bs = out_bs;
   p.B = (int)B; p.tiles = 0; p.k = *k;
+  p.lpq = lp_quant(n, k->two_var);
   p.philox_seed = p.philox_offset = 0ull;
   p.philox_state = nullptr;
   p.loss = LossParams{nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 1};

@@ -36,8 +36,8 @@ def _rel(a, b):
 @pytest.mark.parametrize("far", [1.0, 10.0, 20.0, 25.0, 100.0, 1000.0, 1e5])
 def test_logprob_finite_for_far_samples(far, dtype):
     """x_next = mean + far * s * eps: mean(d^2 / 2 s^2) ~ far^2 / 2 = 0.5 ... 5e5.  The packed Q8.32 field holds 255; everything
-    above travels through the side accumulators (Q39.24 up to 2^27 per CTA, integer units up to 2^50).  Reference: finite, =
-    the oracle's value."""
+    above travels through the side accumulators (a warp with a thread beyond the fixed-point range: Q39.24 up to 2^24 per warp,
+    integer units up to 2^48).  Reference: finite, = the oracle's value."""
     from mixgrpo_b200 import sampling_utils as su
     d = _dev()
     g = torch.Generator().manual_seed(int(far))

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ode_exp_kernel(const __grid_con
   for (int u = 0; u < UNROLL; ++u) if (off[u] < n) ld_stream(vp + off[u], v[u]);
   pdl_prologue();
 #pragma unroll
-  for (int u = 0; u < UNROLL; ++u) if (off[u] < n) ld_stream(xp + off[u], x[u]);
+  for (int u = 0; u < UNROLL; ++u) if (off[u] < n) ld_dep(xp + off[u], x[u]);        // coherent, behind the wait (common.cuh)
   float acc = 0.f;
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u) {
