@@ -445,6 +445,7 @@ def measure_roofline(dev, peak_gbs, peak_kind):
             "kernel": "mg::step_kernel<flow, bf16, SRC_DETERMINISTIC, OUT=0, HALF> — the Euler-ODE sampler step + log-prob (x, v -> x_next, log_prob: 10 B/elem), 21 of a step's 29 launches and the largest share of its device time; launched as the rollout launches it (128-thread CTAs of one half-tile, log-prob sums accumulated as integers, one finalize launch per 25 step launches, its time included)",
             "achieved": top["GBps"], "peak": peak_gbs, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
             "unit": "GB/s", "frac": round(top["GBps"] / peak_gbs, 4), "traffic": None, "us_per_launch": top["us_per_launch"],
+            "peak_note": "the measured peak is a COPY (1 byte written per byte read); a sampler step reads 1.5-2x what it writes and, chained by programmatic dependent launch, requests its model output while the previous launch drains — so read-heavy rows under `kernels` / `kernels_by_group_size` can sit at or slightly above 1.0 of this denominator (HBM3e nominal ~7.7 TB/s)",
             "algorithmic_bytes_per_launch": e * bytes_per_elem("ode", False),
             "how": "CUDA events around 20 replays of a CUDA graph of 25 launches + 1 finalize cycling through 10 buffer sets (10 x (6.3 + 12.6 + 12.6) MB > L2: every input is cold), launched as the step launches it (PDL: model-output loads ahead of the dependency wait, the latents — which inside a rollout chain the previous launch wrote — behind it; deferred log-prob finalization)",
             "step_weighted": {"achieved": round(tot_b / tot_us / 1e3, 1), "frac": round(tot_b / tot_us / 1e3 / peak_gbs, 4), "bytes": tot_b, "us": round(tot_us, 2),

@@ -83,6 +83,15 @@ def test_host_side_argument_validation_needs_no_gpu():
     assert lib.mixgrpo_peer_region_open(None, None) == -1
     old = lib.mixgrpo_set_tuning(2, 1234)
     assert lib.mixgrpo_set_tuning(2, old) == 1234
+    # CTA-shape knobs (ABI v6): key 6 = deferred step launches as 128-thread CTAs (0 never | 1 auto | 2 always), key 7 = CTA size of the
+    # backward kernels (128 | 256), key 8 = read-only launch counter; a CTA cap above 2047 per sample no longer fits the packed word
+    assert lib.mixgrpo_set_tuning(6, 3) == -1 and lib.mixgrpo_set_tuning(6, -1) == -1
+    assert lib.mixgrpo_set_tuning(6, 2) == 1 and lib.mixgrpo_set_tuning(6, 1) == 2
+    assert lib.mixgrpo_set_tuning(7, 64) == -1 and lib.mixgrpo_set_tuning(7, 128) == 256 and lib.mixgrpo_set_tuning(7, 256) == 128
+    assert lib.mixgrpo_set_tuning(8, 0) >= 0
+    assert lib.mixgrpo_set_tuning(0, 2048) == -1 and lib.mixgrpo_set_tuning(0, 2047) == 2047
+    # a deferred launch needs the eight-records-per-sample block: the plain workspace size is refused before any launch
+    assert lib.mixgrpo_flow_step(1, 1, 1, 8, None, None, 0, 1, 8, None, None, None, 1, 512, 12, 8, ctypes.byref(k), 2, _cabi.FLAG_DEFER_LOGP, None, None) == -3
 
 
 def test_python_layer_refuses_cpu_tensors():
