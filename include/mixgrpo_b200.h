@@ -158,7 +158,11 @@ const char* mixgrpo_error_string(int code);    /* text for a return code (cudaGe
  *   x_next_out,out_bs   fp32 (B,n) or NULL      x0_out  fp32 (B,n) contiguous or NULL
  *   mean_out        fp32 (B,n) contiguous or NULL (the 5-tuple's prev_sample_mean, SU:210)
  *   logp_out        fp32 [B] or NULL
- *   workspace       >= mixgrpo_step_workspace_bytes(B,n), zeroed once at allocation
+ *   workspace       >= mixgrpo_step_workspace_bytes(B,n), zeroed once at allocation; with MIXGRPO_FLAG_DEFER_LOGP the launch's own
+ *                   >= mixgrpo_deferred_workspace_bytes(B,n) block (MIXGRPO_ENOSPACE otherwise)
+ *   ordering        x, x_next_in, m1, m2 may have been written by the launch immediately before on the stream (they are read
+ *                   with coherent loads behind the dependency wait); v and noise must not have been when a
+ *                   MIXGRPO_FLAG_PDL_EARLY_* flag is passed (they are requested before it, through the read-only path)
  */
 /* Optional second output of a step launch (nullable `ext`): the latents handed to the VAE, i.e. what the reference
  * computes after the rollout with two more passes over the final latent — unpack_latents (TR:102-115) then

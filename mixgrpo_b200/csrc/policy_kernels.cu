@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, PF ? 3 : 6) policy_step_kernel(const
   float* s_gs = reinterpret_cast<float*>(s_e0 + Kmax);                   // [Kmax] (dL/dlogp / n) / (2 s^2) of the tile's sample
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // tile bookkeeping in 32 bits: T = B * tps < 65536 * 4096, in-sample offsets < 4095 * 2048 + 2048
+  // tile bookkeeping in 32 bits: T = B * tps < 65536 * 2048, in-sample offsets < 2047 * 2048 + 2048
   const int t_lo = (int)(((long long)blockIdx.x * p.T) / gridDim.x), t_hi = (int)(((long long)(blockIdx.x + 1) * p.T) / gridDim.x);
   const int K = t_hi - t_lo;                                             // 1 <= K <= Kmax (host guarantees G <= T)
   const int n = (int)p.n;
