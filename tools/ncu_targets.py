@@ -7,9 +7,9 @@
 
 Launch order (3 launches each, rotating buffer sets so no input is hot in L2 beyond what ncu's cache control leaves); the
 rollout's step launches are issued as the rollout issues them — log-prob sums accumulated (MIXGRPO_FLAG_DEFER_LOGP), ONE finalize:
-  0. first step: bf16 latent in, all_latents[:, 0] and [:, 1] out   mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0,EXT=2>   (1 launch per step)
-  1. Euler-ODE sampler step + log-prob        mg::step_kernel<flow,bf16,SRC_DETERMINISTIC,OUT=0>   (21 of a step's 29 launches)
-  2. SDE sampler step + log-prob, no x0       mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0>           (3 launches)
+  0. first step: bf16 latent in, all_latents[:, 0] and [:, 1] out   mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0,EXT=2,HALF>   (1 launch per step)
+  1. Euler-ODE sampler step + log-prob        mg::step_kernel<flow,bf16,SRC_DETERMINISTIC,OUT=0,HALF>   (21 of a step's 29 launches; 128-thread CTAs)
+  2. SDE sampler step + log-prob, no x0       mg::step_kernel<flow,bf16,SRC_NOISE,OUT=0,HALF>           (3 launches)
   2b. mg::logp_finalize_kernel                                                                   (1 launch)
   3. window forward, 4 items in one launch    mg::policy_fwd_multi_kernel<flow,bf16>               (1 launch)
   4. window backward, 4 items in one launch   mg::policy_bwd_multi_kernel<flow,bf16>               (1 launch)
