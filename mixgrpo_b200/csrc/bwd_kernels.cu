@@ -26,7 +26,8 @@ struct BwdParams {
 // EARLY (MIXGRPO_FLAG_PDL_EARLY_LOADS): the caller guarantees that v / x / x_next were not written by the kernel
 // launched immediately before this one (true right after mixgrpo_policy_fwd, which only writes log-probs), so their
 // loads are issued BEFORE griddepcontrol.wait and overlap the predecessor's tail; only dL/dlogp is read after it.
-template <int FAM, class VT, bool RND, int VEC, bool EARLY>
+// FUSED (compile time): dL/dlogp comes from the clipped-ratio loss evaluated in place (policy path) instead of a given gradient
+template <int FAM, class VT, bool RND, int VEC, bool EARLY, bool FUSED>
 __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_constant__ BwdParams p) {
   if constexpr (!EARLY) pdl_prologue();
   const int b = blockIdx.y;
@@ -40,11 +41,23 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
     ld_dep(p.x_next + (long long)b * p.in_bs + idx, xn);
   }
   if constexpr (EARLY) pdl_prologue();
+  // (g/n)/(2 s^2): per-SAMPLE scalar, same two divisions autograd performs.  With the fused loss (TR:560-585 evaluated in place:
+  // exp, four divisions, the clip logic — ~70 of a thread's ~250 instructions, and the window backward issues on 69 % of its
+  // cycles) ONE thread per CTA evaluates it while the loads are in flight; a plain dL/dlogp is cheaper to read per thread than to
+  // pass through a barrier (measured: 7.1 vs 7.6 us).
+  float gs;
+  if constexpr (FUSED) {
+    __shared__ float s_gs;
+    if (threadIdx.x == 0) {
+      const float g_lp = loss_terms(ld_dep(p.grad_logp + b), ld_dep(p.loss.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;
+      s_gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), p.k.two_var);
+    }
+    __syncthreads();
+    gs = s_gs;
+  } else {
+    gs = __fdiv_rn(__fdiv_rn(ld_dep(p.grad_logp + b), (float)p.n), p.k.two_var);   // the forward launched just before may have written it: coherent
+  }
   if (!active) return;
-  // (g/n)/(2 s^2): per-sample scalar, same two divisions autograd performs
-  float g_lp = ld_dep(p.grad_logp + b);            // the forward launched just before wrote it: behind the wait, coherent
-  if (p.loss.old_lp) g_lp = loss_terms(g_lp, ld_dep(p.loss.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;   // TR:560-585 in place
-  const float gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), p.k.two_var);
 
   if constexpr (FAM == 0) {   // flow, SU:186
 #pragma unroll
@@ -110,18 +123,23 @@ __global__ void __launch_bounds__(kThreads) logprob_bwd_kernel(const __grid_cons
   st_stream(reinterpret_cast<VT*>(p.grad_v) + (long long)b * p.n + idx, g);   // bf16 store rounds (RNE)
 }
 
-template <int FAM, class VT, bool RND>
-static int launch_bwd(const BwdParams& p, int64_t B, bool vec, bool early, cudaStream_t st) {
+template <int FAM, class VT, bool RND, bool FUSED>
+static int launch_bwd_f(const BwdParams& p, int64_t B, bool vec, bool early, cudaStream_t st) {
   const int thr = g_bwd_threads;
   if (vec) {
     dim3 grid((unsigned)((p.n + (long long)thr * kVec - 1) / ((long long)thr * kVec)), (unsigned)B);
-    if (early) launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, true>, grid, thr, 0, st, p);
-    else launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, false>, grid, thr, 0, st, p);
+    if (early) launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, true, FUSED>, grid, thr, 0, st, p);
+    else launch_pdl(logprob_bwd_kernel<FAM, VT, RND, kVec, false, FUSED>, grid, thr, 0, st, p);
   } else {
     dim3 grid((unsigned)((p.n + thr - 1) / thr), (unsigned)B);
-    launch_pdl(logprob_bwd_kernel<FAM, VT, RND, 1, false>, grid, thr, 0, st, p);
+    launch_pdl(logprob_bwd_kernel<FAM, VT, RND, 1, false, FUSED>, grid, thr, 0, st, p);
   }
   return (int)cudaGetLastError();
+}
+
+template <int FAM, class VT, bool RND>
+static int launch_bwd(const BwdParams& p, int64_t B, bool vec, bool early, cudaStream_t st) {
+  return p.loss.old_lp ? launch_bwd_f<FAM, VT, RND, true>(p, B, vec, early, st) : launch_bwd_f<FAM, VT, RND, false>(p, B, vec, early, st);
 }
 
 template <int FAM>

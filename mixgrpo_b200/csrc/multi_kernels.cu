@@ -103,9 +103,15 @@ __global__ void __launch_bounds__(kThreads) policy_bwd_multi_kernel(const __grid
     ld_dep(q.x_in + (long long)b * q.in_bs + idx, xn);
   }
   if (p.early != 0) pdl_prologue();
+  // dL/dlogp and (g/n)/(2 s^2) are per-SAMPLE scalars: ONE thread per CTA evaluates them while the loads are in flight
+  __shared__ float s_gs;
+  if (threadIdx.x == 0) {
+    const float g_lp = loss_terms(ld_dep(q.logp + b), ld_dep(q.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;   // the forward just wrote logp
+    s_gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), q.k.two_var);
+  }
+  __syncthreads();
   if (!active) return;
-  const float g_lp = loss_terms(ld_dep(q.logp + b), ld_dep(q.old_lp + b), ld_dep(p.loss.adv + b), p.loss, 1.f).grad;   // the forward just wrote logp
-  const float gs = __fdiv_rn(__fdiv_rn(g_lp, (float)p.n), q.k.two_var);
+  const float gs = s_gs;
   if constexpr (FAM == kFlow) {
 #pragma unroll
     for (int i = 0; i < kVec; ++i) t[i] = __fmul_rn(v[i], c[2]);
