@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, FAM == kDance ? 4 : 6) policy_fwd_mu
 
 // the chain of mg::logprob_bwd_kernel (csrc/bwd_kernels.cu), item-indexed; dL/dlogp is evaluated in place (TR:560-585)
 template <int FAM, class VT, bool RND>
-__global__ void __launch_bounds__(kThreads) policy_bwd_multi_kernel(const __grid_constant__ MultiParams p) {
+__global__ void __launch_bounds__(kThreads, 6) policy_bwd_multi_kernel(const __grid_constant__ MultiParams p) {
   if (p.early == 0) pdl_prologue();
   const int item = blockIdx.y / p.B, b = blockIdx.y - item * p.B;
   const MultiItem& q = p.it[item];
