@@ -6,16 +6,18 @@ int g_max_ctas_per_sample = kMaxCtasPerSample;          // bench knob (mixgrpo_s
 int g_use_pdl = 1;                                      // bench knob (key 1): programmatic dependent launch on/off
 int g_bwd_threads = kThreads;                           // knob (key 7): CTA size of the log-prob backward kernels
 int g_half_ctas = 1;                                    // knob (key 6): deferred launches in the 128-thread shape (0 never, 1 auto, 2 always)
-long long g_half_launches = 0;
+std::atomic<long long> g_half_launches{0};             // host threads of one process may launch concurrently
 int sm_count() {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[64];               // zero-initialised; two threads may both fill an entry with the same value
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] == 0) {
+  int sms = cached[dev].load(std::memory_order_relaxed);
+  if (sms == 0) {
     int n = 0;
-    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    sms = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    cached[dev].store(sms, std::memory_order_relaxed);
   }
-  return cached[dev];
+  return sms;
 }
 int policy_fwd_dance(StepParams& p, int v_dtype, int64_t B, bool vec, bool rnd, cudaStream_t st);   // step_dance.cu
 }  // namespace mg
@@ -39,7 +41,7 @@ extern "C" __attribute__((visibility("default"))) int64_t mixgrpo_deferred_works
 extern "C" __attribute__((visibility("default"))) int mixgrpo_set_tuning(int key, int value) {
   if (key == 2) return value < 0 ? MIXGRPO_EINVAL : mixgrpo_peer_set_timeout_ms(value);
   if (key >= 3 && key <= 5) return mixgrpo_policy_set_tuning(key, value);
-  if (key == 8) return (int)(g_half_launches & 0x7fffffff);       // read-only: launches issued in the 128-thread shape
+  if (key == 8) return (int)(g_half_launches.load(std::memory_order_relaxed) & 0x7fffffff);       // read-only: launches issued in the 128-thread shape
   if (key == 7) {
     if (value != kThreads && value != kHalfThreads) return MIXGRPO_EINVAL;
     const int old = g_bwd_threads;

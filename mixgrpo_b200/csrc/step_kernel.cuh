@@ -19,6 +19,8 @@
 // or — a rollout's deferred launches — nobody does and one finalize launch writes all log-probs.  Details at step_kernel below
 // and in step_math.cuh.
 #pragma once
+#include <atomic>
+
 #include "step_math.cuh"
 
 namespace mg {
@@ -259,7 +261,7 @@ extern int g_max_ctas_per_sample;                       // bench knob (mixgrpo_s
 extern int g_half_ctas;                                 // knob (key 6): deferred launches use the 128-thread shape — 0 never, 1 when the
                                                         // 256-thread grid exceeds one wave (default), 2 always
 int sm_count();                                         // SMs of the current device (cached), step_flow.cu
-extern long long g_half_launches;                       // launches issued in the 128-thread shape so far (key 8 reads it)
+extern std::atomic<long long> g_half_launches;          // launches issued in the 128-thread shape so far (key 8 reads it)
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -273,7 +275,7 @@ static int launch(StepParams& p, cudaStream_t st) {
     // (24,4096,64) -4 % on the whole step; a sub-wave grid, (24,1024,64) = 768 CTAs, is 0.25 us SLOWER with twice the CTAs to dispatch
     if (p.defer && ctas == p.tiles && (g_half_ctas == 2 || (g_half_ctas == 1 && (long long)ctas * p.B > 6LL * sm_count()))) {
       p.tiles = (int)((p.n + kHalfTile - 1) / kHalfTile);
-      ++g_half_launches;
+      g_half_launches.fetch_add(1, std::memory_order_relaxed);
       dim3 grid((unsigned)p.tiles, (unsigned)p.B);
       launch_pdl(step_kernel<FAM, VT, NT, SRC, ORDER, RND, SDE, true, OUT, EXT, true>, grid, kHalfThreads, 0, st, p);
       return (int)cudaGetLastError();

@@ -18,7 +18,7 @@ int mixgrpo_peer_set_timeout_ms(int) { return 0; }
 int mixgrpo_policy_set_tuning(int, int) { return 0; }
 extern "C" int64_t mixgrpo_step_workspace_bytes(int64_t B, int64_t) { return B * 32; }
 extern "C" int64_t mixgrpo_deferred_workspace_bytes(int64_t B, int64_t) { return B * 256; }
-namespace mg { int g_half_ctas = 0; long long g_half_launches = 0; int g_bwd_threads = 256; int sm_count() { return 148; } }
+namespace mg { int g_half_ctas = 0; std::atomic<long long> g_half_launches{0}; int g_bwd_threads = 256; int sm_count() { return 148; } }
 
 using namespace mg;
 
