@@ -208,3 +208,36 @@ def test_train_timesteps_use_fp32_product_like_the_reference(shift):
         assert smp["timesteps"].tolist() == [ref[:-1]] * 2
     if shift in (1.0, 3.0):
         assert differs_from_double > 0                                          # the sweep does cover the off-by-one cases
+
+
+def test_fixed_point_logprob_reduction_error_model():
+    """The kernels' log-prob reduction (csrc/step_math.cuh) is integer from the thread up: a thread's fp32 sum of d^2 over its 8 scalars
+    is scaled by 2^32 / (n * 2 s^2) and rounded to an integer, everything above is exact integer addition.  Restated here on the CPU
+    (torch fp32 for the per-thread part, int64 above) against the fp64 mean: the claimed 0.29 * sqrt(n / 8) units of 2^-32 (1.2e-8 at
+    1024^2) of quantisation holds on top of the fp32 rounding of the scale itself, for on-policy residuals and for a policy that has drifted to |d|/s ~ 5; the per-thread cap leaves the fast path
+    more than a factor 10 of headroom over the largest on-policy thread share at both ends of the size range."""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    for n, spread in ((4096 * 64, 1.0), (4096 * 64, 5.0), (256 * 64, 1.0), (1024 * 64, 3.0)):
+        B, two_var = 3, 2.0 * 0.31 ** 2
+        d = torch.randn(B, n, generator=g) * (0.31 * spread)
+        denom = torch.tensor(float(n), dtype=torch.float32) * torch.tensor(two_var, dtype=torch.float32)     # lp_quant(): three IEEE single ops
+        scale = torch.tensor(4294967296.0, dtype=torch.float32) / denom
+        fit = 1095216660480.0 / float((n + 7) // 8)
+        cap = min(fit, 67108864.0)
+        dd = (d * d).view(B, n // 8, 4, 2)
+        acc = torch.zeros(B, n // 8)
+        for j in range(4):                                     # acc += dd[2j] + dd[2j+1], pair-wise, in order
+            acc = acc + (dd[:, :, j, 0] + dd[:, :, j, 1])
+        u = acc * scale
+        assert float(u.max()) * 10 < cap or spread > 1.0       # on-policy: the LARGEST thread share is > 10x below the cap (19x at 256^2, 150x at 1024^2)
+        assert float(u.max()) < cap                            # all of these stay on the fast path
+        q = torch.round(u.double()).to(torch.int64).sum(dim=1)  # round-to-nearest-even like cvt.rni, then exact integer sums
+        got = q.double() / 4294967296.0
+        want = (d.double() ** 2).sum(dim=1) / (float(n) * two_var)
+        err = (got - want).abs().max().item()
+        # quantisation 0.29 * sqrt(n/8) * 2^-32 (random, absolute) plus what any fp32 evaluation has: the scale is two fp32 roundings
+        # of n * 2 s^2 (systematic, relative <= 2^-23) and each thread's own 8-term sum carries relative 2^-24 (random)
+        bound = 4 * (0.29 * (n / 8) ** 0.5 / 4294967296.0) + float(want.max()) * 2.0 ** -23
+        assert err < bound, (n, spread, err, bound)
+        assert err < 1.2e-7 * max(1.0, float(want.max()))      # one fp32 ulp of the quantity it feeds
